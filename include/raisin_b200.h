@@ -1,0 +1,124 @@
+/*
+ * raisin_b200.h — C ABI of libraisin_b200.so: the B200 (sm_100a) implementation of
+ * go-compression/raisin's LZSS + Huffman hot path.
+ *
+ * These entry points are what a cgo shim inside the reference's compressor/lz and
+ * compressor/huffman packages binds (see INTEGRATION.md and go/).  Each one names the
+ * reference function whose body it replaces.  Plain pointers and sizes only; no torch
+ * types.  All functions are re-entrant from multiple OS threads (the reference's
+ * BenchmarkSuite calls the codecs from several goroutines at once, engine/engine.go:235-244);
+ * the library keeps no global mutable codec state (deliberately unlike
+ * compressor/huffman/huffman.go:56,129).
+ *
+ * There is NO CPU fallback: every codec call runs on the CUDA device or fails with
+ * RSN_ERR_CUDA / RSN_ERR_NO_DEVICE.
+ *
+ * Error convention: 0 on success, negative code on failure.  The reference signals the
+ * same conditions by panicking; a shim turns rc != 0 into panic(rsn_strerror(rc)) so that
+ * engine.AsyncBenchmarkFile's recover() (engine/engine.go:315-328) still reports "Failed".
+ */
+#ifndef RAISIN_B200_H
+#define RAISIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSN_OK 0
+#define RSN_ERR_CUDA (-1)              /* a CUDA runtime call failed; see rsn_last_cuda_error() */
+#define RSN_ERR_NO_DEVICE (-2)         /* no usable CUDA device */
+#define RSN_ERR_NOMEM (-3)
+#define RSN_ERR_INVALID_ARG (-4)
+#define RSN_ERR_UNSUPPORTED (-5)       /* valid for the reference, outside this build's limits (documented) */
+#define RSN_ERR_EMPTY_INPUT (-10)      /* huffman.Compress(empty): heap.Pop on empty heap panics (huffman.go:102) */
+#define RSN_ERR_NO_SEPARATOR (-11)     /* huffman decode: no 5C 0A => sections[1] panics (huffman.go:261-264) */
+#define RSN_ERR_BAD_HEADER (-12)       /* decodeTree index out of range (huffman.go:210) / empty table */
+#define RSN_ERR_TRUNCATED (-13)        /* findCodes reads data[max] (huffman.go:145) / pad > bits (huffman.go:294) */
+#define RSN_ERR_GUARD (-14)            /* "Max recursion depth" (huffman.go:132-134); strict_limits only */
+#define RSN_ERR_BAD_REFERENCE (-15)    /* lz.Decompress slice out of range (lzss.go:349-350) */
+#define RSN_ERR_SINGLE_LEAF_LOOP (-16) /* single-leaf tree with bits left: unbounded recursion (huffman.go:139-140) */
+
+/* LZSS variants of the reference */
+#define RSN_LZSS_ASYNC 0 /* lz.CompressAsync (lzss.go:109) — what lz.NewWriter / the engine use */
+#define RSN_LZSS_ITER 1  /* lz.Compress      (lzss.go:224) — exported iterative variant */
+
+/* ---- library lifetime ------------------------------------------------------------------ */
+
+/* Select the CUDA device for the calling thread's context (default: current device / 0). */
+int rsn_init(int device);
+/* Release every cached device/pinned buffer of the calling thread's context. */
+void rsn_shutdown(void);
+const char *rsn_strerror(int rc);
+/* Text of the last CUDA error seen by the calling thread ("" if none). */
+const char *rsn_last_cuda_error(void);
+/* Release a buffer returned through an `out` parameter of the host-buffer API. */
+void rsn_free(void *p);
+/* Pinned host allocation helpers (optional; any host pointer is accepted as input). */
+void *rsn_host_alloc(size_t n);
+void rsn_host_free(void *p);
+
+/* ---- host-buffer API: what the cgo shim binds ------------------------------------------- */
+
+/*
+ * Replaces the bodies of lz.CompressAsync (lzss.go:109-154, variant RSN_LZSS_ASYNC) and
+ * lz.Compress (lzss.go:224-316, variant RSN_LZSS_ITER).  `window` is maxSearchBufferLength
+ * (lz.NewWriter passes DefaultWindowSize = 4096, lzss.go:35-40); window <= 0 means an
+ * unbounded search buffer exactly as in the reference (lzss.go:125, 249).
+ * `in` is only read during the call.  `*out` is library-owned; release with rsn_free().
+ */
+int rsn_lzss_compress(const uint8_t *in, size_t n, int64_t window, int variant, uint8_t **out, size_t *out_n);
+/* Replaces lz.Decompress (lzss.go:323-364). */
+int rsn_lzss_decompress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
+/* Replaces huffman.Compress (huffman.go:299-325). */
+int rsn_huff_compress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
+/*
+ * Replaces huffman.Decompress (huffman.go:327-330).  strict_limits != 0 reproduces the
+ * reference's 900000-bit recursion guard as RSN_ERR_GUARD; 0 lifts it.
+ */
+int rsn_huff_decompress(const uint8_t *in, size_t n, int strict_limits, uint8_t **out, size_t *out_n);
+
+/*
+ * engine.compress / engine.decompress (engine/engine.go:443-479) for a layer list such as
+ * "lzss,huffman": compress applies the algorithms left to right, decompress right to left.
+ * Intermediate buffers stay on the device.  Only "lzss" and "huffman" are known names.
+ */
+int rsn_compress_layers(const char *algorithms, const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
+int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
+
+/* ---- device-buffer API ------------------------------------------------------------------- */
+/*
+ * Same operations with input and output resident in device memory of the context's device.
+ * `stream` is a cudaStream_t (NULL = the context's own stream).  `*d_out` is allocated by the
+ * library (stream-ordered); release with rsn_dev_free().  The calls synchronise the stream
+ * where the algorithm needs a size on the host (documented in DESIGN.md).
+ */
+int rsn_dev_lzss_compress(const uint8_t *d_in, size_t n, int64_t window, int variant, uint8_t **d_out, size_t *out_n,
+                          void *stream);
+int rsn_dev_lzss_decompress(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, void *stream);
+int rsn_dev_huff_compress(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, void *stream);
+int rsn_dev_huff_decompress(const uint8_t *d_in, size_t n, int strict_limits, uint8_t **d_out, size_t *out_n,
+                            void *stream);
+void rsn_dev_free(void *d_ptr, void *stream);
+
+/*
+ * Per-position match arrays of variant A over an already-escaped device buffer: for each i,
+ * packed[i] = (len << 16) | off as computed by compressorWorker (lzss.go:166-184).
+ * Exposed for parity tests and for the position-range sharded path.  window in [1, 65535].
+ */
+int rsn_dev_lzss_match(const uint8_t *d_enc, size_t n, int64_t window, uint32_t *d_packed, void *stream);
+
+/* ---- introspection ----------------------------------------------------------------------- */
+
+/* Number of kernels this library has launched from the calling thread since the last reset. */
+uint64_t rsn_kernel_launches(void);
+void rsn_reset_kernel_launches(void);
+/* "raisin_b200 <version> sm_100a" */
+const char *rsn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

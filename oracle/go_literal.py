@@ -509,10 +509,12 @@ def decodeTree(tree: bytes):  # huffman.go:196-227
                 symFreqs[10] = freq
                 i += 1
             else:
-                for j, c in go_range_string(tree):
-                    if j == i + 1:
-                        symFreqs[c] = freq
-                        break
+                # Go: `for j, c := range tree { if j == i+1 {...; break} }` rescans from 0.
+                # tree[i] is ASCII '|', so i+1 is always a rune boundary of that scan and the
+                # rune found there equals the one decoded directly at i+1.
+                for j, c in go_range_string(tree[i + 1 : i + 5]):
+                    symFreqs[c] = freq
+                    break
             i += 1
         i += 1
     return symFreqs

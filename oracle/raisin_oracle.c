@@ -185,20 +185,38 @@ static void match_at(const uint8_t *enc, size_t n, int64_t window, int mode, siz
     if (window > 0 && i > (size_t)window) ws = i - (size_t)window; /* lzss.go:123-127 */
     const uint8_t *win = enc + ws;
     size_t wn = i - ws;
-    size_t best = 0, best_idx = 0, from = 0;
-    for (size_t k = 1; i + k <= n; k++) {
-        ptrdiff_t idx;
-        if (mode == 0) {
-            /* leftmost hit of a longer pattern is never left of the shorter one's */
-            idx = bytes_index(win + from, wn - from, enc + i, k);
-            if (idx >= 0) idx += (ptrdiff_t)from;
-        } else {
-            idx = bytes_index(win, wn, enc + i, k);
+    size_t best = 0, best_idx = 0;
+    if (mode != 0) {
+        /* literal: one more byte per level, each level a fresh leftmost search (bytes.Index) */
+        for (size_t k = 1; i + k <= n; k++) {
+            ptrdiff_t idx = bytes_index(win, wn, enc + i, k);
+            if (idx < 0) break;
+            best = k;
+            best_idx = (size_t)idx;
         }
-        if (idx < 0) break;
-        best = k;
-        best_idx = (size_t)idx;
-        from = best_idx;
+    } else {
+        /*
+         * Same result, fewer searches: "enc[i:i+k] occurs in win" is monotone in k (a prefix of
+         * an occurring pattern occurs), so the deepest found level is the largest such k; find
+         * it by doubling then bisection, then take the leftmost hit of that k.
+         */
+        size_t kmax = n - i < wn ? n - i : wn;
+        size_t lo = 0, hi = 1; /* invariant: lo occurs (lo = 0 trivially), answer < hi+... */
+        while (hi <= kmax && bytes_index(win, wn, enc + i, hi) >= 0) {
+            lo = hi;
+            hi *= 2;
+        }
+        if (hi > kmax) hi = kmax + 1;
+        /* largest k in [lo, hi) that occurs */
+        while (lo + 1 < hi) {
+            size_t mid = lo + (hi - lo) / 2;
+            if (bytes_index(win, wn, enc + i, mid) >= 0)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        best = lo;
+        if (best) best_idx = (size_t)bytes_index(win, wn, enc + i, best);
     }
     *len_out = (uint32_t)best;
     *off_out = best ? (uint32_t)(wn - best_idx) : 0;

@@ -49,8 +49,9 @@ int rsno_unescape(const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
  * len_out[i] = size of the longest pattern enc[i:i+k] found by bytes.Index in the window
  * enc[max(0,i-W):i] (W<=0: unbounded), 0 if even one byte is not found;
  * off_out[i] = len(window) - leftmost index of that pattern (0 when len is 0).
- * mode 0: resume search from the previous hit (same result, faster); mode 1: literal
- * (every extension re-runs the leftmost search from the window start, as bytes.Index does).
+ * mode 1: literal (the pattern grows one byte per level and every level re-runs the leftmost
+ * search from the window start, as the reference's recursion does); mode 0: same result by
+ * monotonicity (doubling + bisection on the length, then one leftmost search).
  * threads >= 1 splits positions over pthreads (the goroutine-per-byte analogue).
  */
 int rsno_lzss_match_arrays(const uint8_t *enc, size_t n, int64_t window, int mode, int threads,

@@ -1,0 +1,202 @@
+// api.cu — the C ABI (include/raisin_b200.h): host-buffer entry points a cgo shim binds,
+// device-buffer entry points, and the engine's layer loops.
+#include "common.cuh"
+#include "huff.cuh"
+#include "lzss.cuh"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace rsn {
+
+void *host_out_alloc(size_t n);
+
+static cudaStream_t pick_stream(void *stream) { return stream ? (cudaStream_t)stream : ctx().own_stream; }
+
+// device result -> library-owned pinned host buffer
+static int to_host(uint8_t *d, size_t n, uint8_t **out, size_t *out_n, cudaStream_t s) {
+    uint8_t *h = (uint8_t *)host_out_alloc(n ? n : 1);
+    if (!h) {
+        cudaFreeAsync(d, s);
+        return RSN_ERR_NOMEM;
+    }
+    cudaError_t e = cudaSuccess;
+    if (n) e = cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaFreeAsync(d, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        rsn_free(h);
+        return cuda_fail(e, "to_host", __FILE__, __LINE__);
+    }
+    *out = h;
+    *out_n = n;
+    return RSN_OK;
+}
+
+static int to_device(const uint8_t *in, size_t n, DevBuf &d, cudaStream_t s) {
+    RSN_TRY(d.alloc(n + 64, s));
+    if (n) RSN_CUDA(cudaMemcpyAsync(d.p, in, n, cudaMemcpyHostToDevice, s));
+    return RSN_OK;
+}
+
+enum Algo { ALGO_LZSS, ALGO_HUFFMAN };
+
+static int parse_layers(const char *algorithms, std::vector<Algo> &out) {
+    if (!algorithms) return RSN_ERR_INVALID_ARG;
+    std::string s(algorithms);
+    size_t a = 0;
+    while (a <= s.size()) {
+        size_t b = s.find(',', a);
+        if (b == std::string::npos) b = s.size();
+        std::string name = s.substr(a, b - a);
+        if (name == "lzss") out.push_back(ALGO_LZSS);
+        else if (name == "huffman") out.push_back(ALGO_HUFFMAN);
+        else return RSN_ERR_INVALID_ARG;
+        a = b + 1;
+    }
+    return out.empty() ? RSN_ERR_INVALID_ARG : RSN_OK;
+}
+
+// engine.compress (engine.go:443-452): each algorithm consumes the previous one's output;
+// lz.NewWriter uses CompressAsync with DefaultWindowSize 4096 (lzss.go:37-40, 53-57).
+static int layers_dev(const std::vector<Algo> &algos, bool compress, const uint8_t *d_in, size_t n, uint8_t **d_out,
+                      size_t *out_n, cudaStream_t s) {
+    const uint8_t *cur = d_in;
+    size_t cur_n = n;
+    uint8_t *owned = nullptr;
+    const size_t k = algos.size();
+    for (size_t step = 0; step < k; step++) {
+        const Algo a = compress ? algos[step] : algos[k - 1 - step];
+        uint8_t *next = nullptr;
+        size_t next_n = 0;
+        int rc;
+        if (a == ALGO_LZSS)
+            rc = compress ? lzss_compress_dev(cur, cur_n, 4096, RSN_LZSS_ASYNC, &next, &next_n, s)
+                          : lzss_decompress_dev(cur, cur_n, &next, &next_n, s);
+        else
+            rc = compress ? huff_compress_dev(cur, cur_n, &next, &next_n, s)
+                          : huff_decompress_dev(cur, cur_n, nullptr, 0, &next, &next_n, s);
+        if (owned) cudaFreeAsync(owned, s);
+        owned = nullptr;
+        if (rc != RSN_OK) return rc;
+        owned = next;
+        cur = next;
+        cur_n = next_n;
+    }
+    *d_out = owned;
+    *out_n = cur_n;
+    return RSN_OK;
+}
+
+}  // namespace rsn
+
+using namespace rsn;
+
+extern "C" {
+
+int rsn_lzss_compress(const uint8_t *in, size_t n, int64_t window, int variant, uint8_t **out, size_t *out_n) {
+    if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    cudaStream_t s = ctx().own_stream;
+    DevBuf d;
+    RSN_TRY(to_device(in, n, d, s));
+    uint8_t *r = nullptr;
+    size_t rn = 0;
+    RSN_TRY(lzss_compress_dev(d.as<uint8_t>(), n, window, variant, &r, &rn, s));
+    return to_host(r, rn, out, out_n, s);
+}
+
+int rsn_lzss_decompress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_n) {
+    if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    cudaStream_t s = ctx().own_stream;
+    DevBuf d;
+    RSN_TRY(to_device(in, n, d, s));
+    uint8_t *r = nullptr;
+    size_t rn = 0;
+    RSN_TRY(lzss_decompress_dev(d.as<uint8_t>(), n, &r, &rn, s));
+    return to_host(r, rn, out, out_n, s);
+}
+
+int rsn_huff_compress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_n) {
+    if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    cudaStream_t s = ctx().own_stream;
+    DevBuf d;
+    RSN_TRY(to_device(in, n, d, s));
+    uint8_t *r = nullptr;
+    size_t rn = 0;
+    RSN_TRY(huff_compress_dev(d.as<uint8_t>(), n, &r, &rn, s));
+    return to_host(r, rn, out, out_n, s);
+}
+
+int rsn_huff_decompress(const uint8_t *in, size_t n, int strict_limits, uint8_t **out, size_t *out_n) {
+    if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    cudaStream_t s = ctx().own_stream;
+    DevBuf d;
+    RSN_TRY(to_device(in, n, d, s));
+    uint8_t *r = nullptr;
+    size_t rn = 0;
+    RSN_TRY(huff_decompress_dev(d.as<uint8_t>(), n, in, strict_limits, &r, &rn, s));
+    return to_host(r, rn, out, out_n, s);
+}
+
+static int layers_host(const char *algorithms, bool compress, const uint8_t *in, size_t n, uint8_t **out,
+                       size_t *out_n) {
+    if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
+    std::vector<Algo> algos;
+    RSN_TRY(parse_layers(algorithms, algos));
+    RSN_TRY(ensure_ctx());
+    cudaStream_t s = ctx().own_stream;
+    DevBuf d;
+    RSN_TRY(to_device(in, n, d, s));
+    uint8_t *r = nullptr;
+    size_t rn = 0;
+    RSN_TRY(layers_dev(algos, compress, d.as<uint8_t>(), n, &r, &rn, s));
+    return to_host(r, rn, out, out_n, s);
+}
+
+int rsn_compress_layers(const char *algorithms, const uint8_t *in, size_t n, uint8_t **out, size_t *out_n) {
+    return layers_host(algorithms, true, in, n, out, out_n);
+}
+int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, uint8_t **out, size_t *out_n) {
+    return layers_host(algorithms, false, in, n, out, out_n);
+}
+
+// ---- device-buffer API
+
+int rsn_dev_lzss_compress(const uint8_t *d_in, size_t n, int64_t window, int variant, uint8_t **d_out, size_t *out_n,
+                          void *stream) {
+    if ((!d_in && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    return lzss_compress_dev(d_in, n, window, variant, d_out, out_n, pick_stream(stream));
+}
+int rsn_dev_lzss_decompress(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, void *stream) {
+    if ((!d_in && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    return lzss_decompress_dev(d_in, n, d_out, out_n, pick_stream(stream));
+}
+int rsn_dev_huff_compress(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, void *stream) {
+    if ((!d_in && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    return huff_compress_dev(d_in, n, d_out, out_n, pick_stream(stream));
+}
+int rsn_dev_huff_decompress(const uint8_t *d_in, size_t n, int strict_limits, uint8_t **d_out, size_t *out_n,
+                            void *stream) {
+    if ((!d_in && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    return huff_decompress_dev(d_in, n, nullptr, strict_limits, d_out, out_n, pick_stream(stream));
+}
+
+int rsn_dev_lzss_match(const uint8_t *d_enc, size_t n, int64_t window, uint32_t *d_packed, void *stream) {
+    if ((!d_enc && n) || (!d_packed && n)) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    if (n == 0) return RSN_OK;
+    uint32_t W = 0;
+    RSN_TRY(lzss_effective_window(window, n, &W));
+    return lzss_match(d_enc, n, W, d_packed, pick_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// common.cuh — context, error plumbing and block-level primitives shared by all kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/raisin_b200.h"
+
+namespace rsn {
+
+// ----------------------------------------------------------------------------- context
+
+struct Ctx {
+    int device = -1;
+    cudaStream_t own_stream = nullptr;
+    bool ready = false;
+    uint64_t launches = 0;
+    char cuda_err[256] = {0};
+    // small pinned scratch for scalar read-backs (sizes, flags)
+    uint64_t *h_scalars = nullptr;  // 64 x u64
+};
+
+Ctx &ctx();
+int ensure_ctx();
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define RSN_CUDA(expr)                                                       \
+    do {                                                                     \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) return ::rsn::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define RSN_TRY(expr)            \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != RSN_OK) return _rc; \
+    } while (0)
+
+// kernel launch with launch counting and error check
+#define RSN_LAUNCH(kernel, grid, block, smem, stream, ...)                   \
+    do {                                                                     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
+        ::rsn::ctx().launches++;                                             \
+        RSN_CUDA(cudaGetLastError());                                        \
+    } while (0)
+
+// Stream-ordered device buffer; freed (stream-ordered) on scope exit unless released.
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { reset(); }
+    int alloc(size_t n, cudaStream_t stream);
+    void reset();
+    void *release() {
+        void *q = p;
+        p = nullptr;
+        return q;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ----------------------------------------------------------------------------- geometry
+
+constexpr int kTileThreads = 256;      // threads per CTA for byte-stream kernels
+constexpr int kItems = 16;             // bytes per thread (one uint4 load)
+constexpr int kTile = kTileThreads * kItems;  // 4096 bytes per CTA tile
+
+static inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------- device helpers
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
+
+// Load 16 consecutive bytes starting at base+idx (idx multiple of 16 when base is 16B-aligned);
+// bytes beyond n read as `fill`.  Falls back to byte loads at the ragged end / unaligned base.
+__device__ __forceinline__ void load16(const uint8_t *__restrict__ base, size_t idx, size_t n, uint8_t fill,
+                                       uint8_t (&v)[16]) {
+    if (idx + 16 <= n && ((reinterpret_cast<uintptr_t>(base + idx) & 15) == 0)) {
+        uint4 q = __ldg(reinterpret_cast<const uint4 *>(base + idx));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = (uint8_t)(w[k >> 2] >> ((k & 3) * 8));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = (idx + k < n) ? __ldg(base + idx + k) : fill;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_inclusive_sum(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= (unsigned)d) v += o;
+    }
+    return v;
+}
+
+// Exclusive sum over the CTA (blockDim.x multiple of 32, <= 1024).  Returns the exclusive
+// prefix of `v` and writes the CTA total to `total`.  `smem` must hold 33 T's.
+template <typename T>
+__device__ __forceinline__ T block_exclusive_sum(T v, T *smem, T &total) {
+    const unsigned lane = lane_id(), wid = warp_id();
+    const unsigned nw = (blockDim.x + 31) >> 5;
+    T inc = warp_inclusive_sum(v);
+    if (lane == 31) smem[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        T w = lane < nw ? smem[lane] : T(0);
+        T winc = warp_inclusive_sum(w);
+        smem[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) smem[32] = winc;
+    }
+    __syncthreads();
+    T res = smem[wid] + inc - v;
+    total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+__device__ __forceinline__ int ndig_u32(uint32_t v) {
+    return 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
+           (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+}
+
+#endif  // __CUDACC__
+
+// ----------------------------------------------------------------------------- shared kernels (scan.cu)
+
+// Exclusive scan of per-tile u64 values by one CTA; out[t] = sum(in[0..t)), *total = sum of all.
+int spine_scan_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t *d_total, size_t count, cudaStream_t s);
+// Read one u64 back to the host (synchronises the stream).
+int read_u64(const uint64_t *d_src, uint64_t *h_dst, cudaStream_t s);
+
+}  // namespace rsn

@@ -1,0 +1,237 @@
+// huff_decode.cu — Huffman decompress (huffman.Decompress, huffman.go:327-330, 258-297).
+//
+// The reference stream is ONE bit string with no block structure, so parallel decode has to
+// find code boundaries by itself: every thread decodes its own fixed-size subsequence from a
+// guessed start and we iterate "start[t] = end[t-1]" to a fixed point (self-synchronisation).
+// Subsequence 0 starts at bit 0, which is exact, so the fixed point is the sequential decode
+// of findCodes (huffman.go:131-153): walk from the root, left on 0 / right on 1, emit at a
+// leaf, restart at the root while bits remain, fail if the bits end inside a code.
+#include "common.cuh"
+#include "huff.cuh"
+#include "huff_host.h"
+#include "utf8.cuh"
+
+#include <cstring>
+#include <vector>
+
+namespace rsn {
+
+constexpr uint32_t kSubBits = 256;  // bits per subsequence (one thread)
+
+struct DecParams {
+    const uint8_t *bits;   // payload bytes after the pad byte
+    uint64_t diff;         // pad bits to skip
+    uint64_t max;          // number of code bits
+    const HuffNode *nodes;
+    int32_t root;
+};
+
+__device__ __forceinline__ uint32_t get_bit(const DecParams &p, uint64_t i) {
+    const uint64_t b = p.diff + i;
+    return (__ldg(p.bits + (b >> 3)) >> (7 - (uint32_t)(b & 7))) & 1u;
+}
+
+// Decode codes that START in [pos, limit).  Returns the position after the last complete code
+// (>= limit unless the bits ran out).  `truncated` is set if the bits end inside a code.
+// If OUT is non-null the UTF-8 bytes are written there.
+template <bool WRITE>
+__device__ __forceinline__ uint64_t decode_span(const DecParams &p, uint64_t pos, uint64_t limit, uint64_t &bytes,
+                                                bool &truncated, uint8_t *out) {
+    bytes = 0;
+    truncated = false;
+    while (pos < limit) {
+        int32_t node = p.root;
+        HuffNode nd = p.nodes[node];
+        uint64_t q = pos;
+        while (nd.left >= 0) {
+            if (q >= p.max) {
+                truncated = true;
+                return q;
+            }
+            node = get_bit(p, q) ? nd.right : nd.left;
+            nd = p.nodes[node];
+            q++;
+        }
+        if (WRITE) {
+            bytes += (uint64_t)utf8_encode(nd.right, out + bytes);
+        } else {
+            bytes += (uint64_t)utf8_width(nd.right);
+        }
+        pos = q;
+    }
+    return pos;
+}
+
+__global__ void k_hdec_init(DecParams p, size_t subs, uint64_t *__restrict__ start, uint64_t *__restrict__ end,
+                            uint64_t *__restrict__ cnt) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= subs) return;
+    const uint64_t s0 = (uint64_t)t * kSubBits;
+    const uint64_t limit = min((uint64_t)(t + 1) * kSubBits, p.max);
+    uint64_t bytes;
+    bool trunc;
+    const uint64_t e = decode_span<false>(p, s0, limit, bytes, trunc, nullptr);
+    start[t] = s0;
+    end[t] = e;
+    cnt[t] = bytes;
+}
+
+__global__ void k_hdec_sync(DecParams p, size_t subs, uint64_t *__restrict__ start,
+                            const uint64_t *__restrict__ end_prev, uint64_t *__restrict__ end_next,
+                            uint64_t *__restrict__ cnt, uint32_t *__restrict__ changed) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= subs) return;
+    if (t == 0) {
+        end_next[0] = end_prev[0];
+        return;
+    }
+    const uint64_t s1 = end_prev[t - 1];
+    if (s1 == start[t]) {
+        end_next[t] = end_prev[t];
+        return;
+    }
+    const uint64_t limit = min((uint64_t)(t + 1) * kSubBits, p.max);
+    uint64_t bytes = 0;
+    bool trunc;
+    uint64_t e = s1;
+    if (s1 < limit) e = decode_span<false>(p, s1, limit, bytes, trunc, nullptr);
+    start[t] = s1;
+    end_next[t] = e;
+    cnt[t] = bytes;
+    *changed = 1;
+}
+
+__global__ void k_hdec_write(DecParams p, size_t subs, const uint64_t *__restrict__ start,
+                             const uint64_t *__restrict__ off, uint8_t *__restrict__ out,
+                             uint32_t *__restrict__ err) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= subs) return;
+    const uint64_t limit = min((uint64_t)(t + 1) * kSubBits, p.max);
+    const uint64_t s0 = start[t];
+    if (s0 >= limit) return;
+    uint64_t bytes;
+    bool trunc;
+    decode_span<true>(p, s0, limit, bytes, trunc, out + off[t]);
+    if (trunc) *err = 1;  // data[i] with i == len(data) (huffman.go:145)
+}
+
+int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int strict, uint8_t **d_out, size_t *out_n,
+                        cudaStream_t s) {
+    Ctx &c = ctx();
+    // ---- host: find the first 5C 0A (strings.SplitN, huffman.go:261) and parse the header
+    std::vector<uint8_t> h_copy;
+    const uint8_t *h = h_in;
+    size_t hn = n;
+    auto find_sep = [](const uint8_t *b, size_t len) -> ptrdiff_t {
+        for (size_t i = 0; i + 1 < len; i++)
+            if (b[i] == 0x5C && b[i + 1] == 0x0A) return (ptrdiff_t)i;
+        return -1;
+    };
+    ptrdiff_t sp = -1;
+    if (h) {
+        sp = find_sep(h, n);
+    } else {
+        // device-resident input: pull a prefix, then everything if the header is longer
+        size_t take = n < ((size_t)1 << 20) ? n : ((size_t)1 << 20);
+        for (;;) {
+            h_copy.resize(take);
+            RSN_CUDA(cudaMemcpyAsync(h_copy.data(), d_in, take, cudaMemcpyDeviceToHost, s));
+            RSN_CUDA(cudaStreamSynchronize(s));
+            sp = find_sep(h_copy.data(), take);
+            if (sp >= 0 || take == n) break;
+            take = n;
+        }
+        h = h_copy.data();
+        hn = take;
+    }
+    (void)hn;
+    if (sp < 0) return RSN_ERR_NO_SEPARATOR;
+    std::vector<HuffLeaf> leaves;
+    if (!huff_parse_header(h, (size_t)sp, leaves)) return RSN_ERR_BAD_HEADER;
+    if (leaves.empty()) return RSN_ERR_BAD_HEADER;  // buildTree on an empty map panics
+    HuffTree tree;
+    huff_build_tree(leaves, tree);
+
+    const size_t pay_off = (size_t)sp + 2;
+    const size_t pn = n - pay_off;
+    uint64_t diff = 0;
+    if (pn) {
+        if (h_in) {
+            diff = h_in[pay_off];
+        } else if (pay_off < h_copy.size()) {
+            diff = h_copy[pay_off];
+        } else {
+            uint8_t b = 0;
+            RSN_CUDA(cudaMemcpyAsync(&b, d_in + pay_off, 1, cudaMemcpyDeviceToHost, s));
+            RSN_CUDA(cudaStreamSynchronize(s));
+            diff = b;
+        }
+    }
+    const uint64_t nbits = pn ? (uint64_t)(pn - 1) * 8 : 0;
+    if (diff > nbits) return RSN_ERR_TRUNCATED;  // contentString[int(diff):] out of range
+    const uint64_t max = nbits - diff;
+    if (strict && max > 900000) return RSN_ERR_GUARD;
+
+    DevBuf out;
+    const HuffNode &rootn = tree.nodes[tree.root];
+    if (rootn.left < 0) {  // single-leaf tree: exactly one symbol when no bits remain
+        if (max > 0) return RSN_ERR_SINGLE_LEAF_LOOP;
+        uint8_t u[4];
+        const int w = utf8_encode(rootn.right, u);
+        RSN_TRY(out.alloc(16, s));
+        RSN_CUDA(cudaMemcpyAsync(out.p, u, (size_t)w, cudaMemcpyHostToDevice, s));
+        RSN_CUDA(cudaStreamSynchronize(s));
+        *d_out = (uint8_t *)out.release();
+        *out_n = (size_t)w;
+        return RSN_OK;
+    }
+    if (max == 0) return RSN_ERR_TRUNCATED;  // data[0] on an empty bit string
+
+    DevBuf nodes;
+    RSN_TRY(nodes.alloc(tree.nodes.size() * sizeof(HuffNode), s));
+    RSN_CUDA(cudaMemcpyAsync(nodes.p, tree.nodes.data(), tree.nodes.size() * sizeof(HuffNode), cudaMemcpyHostToDevice, s));
+
+    DecParams p;
+    p.bits = d_in + pay_off + 1;
+    p.diff = diff;
+    p.max = max;
+    p.nodes = nodes.as<HuffNode>();
+    p.root = tree.root;
+
+    const size_t subs = (size_t)div_up(max, kSubBits);
+    DevBuf start, endA, endB, cnt, off, flag;
+    RSN_TRY(start.alloc(subs * 8, s));
+    RSN_TRY(endA.alloc(subs * 8, s));
+    RSN_TRY(endB.alloc(subs * 8, s));
+    RSN_TRY(cnt.alloc(subs * 8, s));
+    RSN_TRY(off.alloc((subs + 1) * 8, s));
+    RSN_TRY(flag.alloc(16, s));
+    const unsigned grid = (unsigned)div_up(subs, 128);
+    RSN_LAUNCH(k_hdec_init, grid, 128, 0, s, p, subs, start.as<uint64_t>(), endA.as<uint64_t>(), cnt.as<uint64_t>());
+    uint64_t *e_prev = endA.as<uint64_t>(), *e_next = endB.as<uint64_t>();
+    for (size_t iter = 0; iter <= subs; iter++) {
+        RSN_CUDA(cudaMemsetAsync(flag.p, 0, 8, s));
+        RSN_LAUNCH(k_hdec_sync, grid, 128, 0, s, p, subs, start.as<uint64_t>(), e_prev, e_next, cnt.as<uint64_t>(),
+                   flag.as<uint32_t>());
+        uint64_t changed = 0;
+        RSN_TRY(read_u64(flag.as<uint64_t>(), &changed, s));
+        std::swap(e_prev, e_next);
+        if (!(uint32_t)changed) break;
+    }
+    RSN_TRY(spine_scan_u64(cnt.as<uint64_t>(), off.as<uint64_t>(), off.as<uint64_t>() + subs, subs, s));
+    uint64_t total = 0;
+    RSN_TRY(read_u64(off.as<uint64_t>() + subs, &total, s));
+    RSN_TRY(out.alloc(total + 16, s));
+    RSN_CUDA(cudaMemsetAsync(flag.p, 0, 8, s));
+    RSN_LAUNCH(k_hdec_write, grid, 128, 0, s, p, subs, start.as<uint64_t>(), off.as<uint64_t>(), out.as<uint8_t>(),
+               flag.as<uint32_t>());
+    uint64_t err = 0;
+    RSN_TRY(read_u64(flag.as<uint64_t>(), &err, s));
+    if ((uint32_t)err) return RSN_ERR_TRUNCATED;
+    (void)c;
+    *d_out = (uint8_t *)out.release();
+    *out_n = (size_t)total;
+    return RSN_OK;
+}
+
+}  // namespace rsn

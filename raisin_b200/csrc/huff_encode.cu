@@ -1,0 +1,303 @@
+// huff_encode.cu — Huffman compress (huffman.Compress, huffman.go:299-325).
+//
+//   K8/K9  rune classify + histogram   (range-over-string at huffman.go:309-311)
+//   host   tree + codes + header        (buildTree 58-103, printCodes 110-127, header 312-318)
+//   K10    code-length scan + bit pack  (encode 229-256, AsByteSlice 174-191: MSB-first,
+//                                        pad zero bits in FRONT of the first payload byte)
+#include "common.cuh"
+#include "huff.cuh"
+#include "huff_host.h"
+#include "utf8.cuh"
+
+#include <vector>
+
+namespace rsn {
+
+constexpr uint32_t kRuneSpace = 0x110000;
+constexpr int kSmallBins = 256;
+
+// bytes base-3 .. base+18 around a thread's 16-byte chunk
+__device__ __forceinline__ void load_chunk_halo(const uint8_t *__restrict__ in, size_t base, size_t n, uint8_t *w) {
+    uint8_t v[16];
+    load16(in, base, n, 0, v);
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k + 3] = v[k];
+#pragma unroll
+    for (int q = 1; q <= 3; q++) w[3 - q] = base >= (size_t)q ? __ldg(in + base - q) : 0;
+#pragma unroll
+    for (int q = 0; q < 3; q++) w[19 + q] = base + 16 + q < n ? __ldg(in + base + 16 + q) : 0;
+}
+
+// ============================================================================= K8/K9 histogram
+
+__global__ void __launch_bounds__(kTileThreads) k_rune_hist(const uint8_t *__restrict__ in, size_t n, size_t tiles,
+                                                            unsigned long long *__restrict__ hist) {
+    __shared__ uint32_t bins[kSmallBins];
+    __shared__ uint32_t fffd_sm;
+    for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x) bins[i] = 0;
+    if (threadIdx.x == 0) fffd_sm = 0;
+    __syncthreads();
+    uint32_t fffd = 0;
+    for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const size_t base = tile * kTile + (size_t)threadIdx.x * kItems;
+        if (base >= n) continue;
+        uint8_t w[22];
+        load_chunk_halo(in, base, n, w);
+        const int valid = (int)min((size_t)16, n - base);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (k < valid) {
+                int32_t r;
+                if (utf8_start_at(w, k, base + k, n, &r)) {
+                    if (r < kSmallBins) atomicAdd(&bins[r], 1u);
+                    else if (r == 0xFFFD) fffd++;
+                    else atomicAdd(&hist[r], 1ull);
+                }
+            }
+        }
+    }
+    // U+FFFD dominates on non-UTF-8 input: keep it out of the atomic paths
+    for (int d = 16; d; d >>= 1) fffd += __shfl_down_sync(0xffffffffu, fffd, d);
+    if (lane_id() == 0 && fffd) atomicAdd(&fffd_sm, fffd);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x)
+        if (bins[i]) atomicAdd(&hist[i], (unsigned long long)bins[i]);
+    if (threadIdx.x == 0 && fffd_sm) atomicAdd(&hist[0xFFFD], (unsigned long long)fffd_sm);
+}
+
+struct RuneFreq {
+    uint32_t rune;
+    uint32_t pad;
+    uint64_t freq;
+};
+
+__global__ void k_hist_compact(const unsigned long long *__restrict__ hist, RuneFreq *__restrict__ list,
+                               unsigned long long *__restrict__ count) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= kRuneSpace) return;
+    const unsigned long long f = hist[r];
+    if (f) {
+        const unsigned long long slot = atomicAdd(count, 1ull);
+        list[slot] = RuneFreq{r, 0, f};
+    }
+}
+
+// ============================================================================= K10 encode
+
+struct CodeEntry {
+    uint32_t rune;
+    uint32_t len;
+    uint64_t code;
+};
+
+__global__ void k_code_scatter(const CodeEntry *__restrict__ list, size_t k, uint64_t *__restrict__ code,
+                               uint8_t *__restrict__ len) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    code[list[i].rune] = list[i].code;
+    len[list[i].rune] = (uint8_t)list[i].len;
+}
+
+// per-tile total code bits
+__global__ void __launch_bounds__(kTileThreads) k_enc_count(const uint8_t *__restrict__ in, size_t n,
+                                                            const uint8_t *__restrict__ len_tab,
+                                                            uint64_t *__restrict__ tile_bits) {
+    __shared__ uint8_t slen[kSmallBins];
+    __shared__ uint32_t sm[33];
+    for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x) slen[i] = len_tab[i];
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
+    uint32_t bits = 0;
+    if (base < n) {
+        uint8_t w[22];
+        load_chunk_halo(in, base, n, w);
+        const int valid = (int)min((size_t)16, n - base);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (k < valid) {
+                int32_t r;
+                if (utf8_start_at(w, k, base + k, n, &r)) bits += r < kSmallBins ? slen[r] : __ldg(len_tab + r);
+            }
+        }
+    }
+    uint32_t total;
+    block_exclusive_sum<uint32_t>(bits, sm, total);
+    if (threadIdx.x == 0) tile_bits[blockIdx.x] = total;
+}
+
+// MSB-first bit writer over a zero-initialised, 4-byte aligned output: partially covered words
+// are merged with atomicOr, fully covered words are stored directly.
+struct BitWriter {
+    uint32_t *out;
+    uint64_t word;   // index of the word being filled
+    uint32_t acc;    // bits so far, left-aligned
+    uint32_t fill;   // bits used in acc
+    bool first;      // current word may be shared with the previous writer
+    __device__ __forceinline__ void init(uint32_t *o, uint64_t bitpos) {
+        out = o;
+        word = bitpos >> 5;
+        fill = (uint32_t)(bitpos & 31);
+        acc = 0;
+        first = fill != 0;
+    }
+    __device__ __forceinline__ void flush_full() {
+        const uint32_t be = __byte_perm(acc, 0, 0x0123);  // big-endian bit order in memory
+        if (first) atomicOr(out + word, be);
+        else out[word] = be;
+        first = false;
+        word++;
+        acc = 0;
+        fill = 0;
+    }
+    __device__ __forceinline__ void put(uint64_t code, uint32_t len) {
+        while (len) {
+            const uint32_t space = 32 - fill;
+            const uint32_t take = len < space ? len : space;
+            const uint32_t bits = (uint32_t)((code >> (len - take)) & ((take == 32) ? 0xFFFFFFFFull : ((1ull << take) - 1)));
+            acc |= bits << (space - take);
+            fill += take;
+            len -= take;
+            if (fill == 32) flush_full();
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (fill) atomicOr(out + word, __byte_perm(acc, 0, 0x0123));
+    }
+};
+
+__global__ void __launch_bounds__(kTileThreads) k_enc_write(const uint8_t *__restrict__ in, size_t n,
+                                                            const uint64_t *__restrict__ code_tab,
+                                                            const uint8_t *__restrict__ len_tab,
+                                                            const uint64_t *__restrict__ tile_bitoff,
+                                                            uint64_t bit_base, uint32_t *__restrict__ out) {
+    __shared__ uint8_t slen[kSmallBins];
+    __shared__ uint64_t scode[kSmallBins];
+    __shared__ uint32_t sm[33];
+    for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x) {
+        slen[i] = len_tab[i];
+        scode[i] = code_tab[i];
+    }
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
+    uint8_t w[22];
+    int valid = 0;
+    uint32_t bits = 0;
+    uint32_t startmask = 0;
+    int32_t runes[16];
+    if (base < n) {
+        load_chunk_halo(in, base, n, w);
+        valid = (int)min((size_t)16, n - base);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            runes[k] = 0;
+            if (k < valid) {
+                int32_t r;
+                if (utf8_start_at(w, k, base + k, n, &r)) {
+                    startmask |= 1u << k;
+                    runes[k] = r;
+                    bits += r < kSmallBins ? slen[r] : __ldg(len_tab + r);
+                }
+            }
+        }
+    }
+    uint32_t total;
+    const uint32_t pre = block_exclusive_sum<uint32_t>(bits, sm, total);
+    if (!startmask) return;
+    BitWriter bw;
+    bw.init(out, bit_base + tile_bitoff[blockIdx.x] + pre);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (startmask & (1u << k)) {
+            const int32_t r = runes[k];
+            if (r < kSmallBins) bw.put(scode[r], slen[r]);
+            else bw.put(__ldg(code_tab + r), __ldg(len_tab + r));
+        }
+    }
+    bw.finish();
+}
+
+// ============================================================================= host orchestration
+
+int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s) {
+    if (n == 0) return RSN_ERR_EMPTY_INPUT;
+    Ctx &c = ctx();
+    const size_t tiles = div_up(n, kTile);
+
+    // ---- histogram
+    DevBuf hist, list, count;
+    RSN_TRY(hist.alloc((size_t)kRuneSpace * 8, s));
+    RSN_TRY(count.alloc(16, s));
+    RSN_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)kRuneSpace * 8, s));
+    RSN_CUDA(cudaMemsetAsync(count.p, 0, 16, s));
+    const unsigned hgrid = (unsigned)min(tiles, (size_t)148 * 8);
+    RSN_LAUNCH(k_rune_hist, hgrid, kTileThreads, 0, s, d_in, n, tiles, hist.as<unsigned long long>());
+    RSN_TRY(list.alloc((size_t)kRuneSpace * sizeof(RuneFreq), s));
+    RSN_LAUNCH(k_hist_compact, (unsigned)div_up(kRuneSpace, 256), 256, 0, s, hist.as<unsigned long long>(),
+               list.as<RuneFreq>(), count.as<unsigned long long>());
+    uint64_t k = 0;
+    RSN_TRY(read_u64(count.as<uint64_t>(), &k, s));
+    std::vector<RuneFreq> h_list(k);
+    RSN_CUDA(cudaMemcpyAsync(h_list.data(), list.p, k * sizeof(RuneFreq), cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    list.reset();
+
+    // ---- host: tree, codes, header (exactly as the reference builds them)
+    std::vector<HuffLeaf> leaves(k);
+    for (size_t i = 0; i < k; i++) leaves[i] = HuffLeaf{(int64_t)h_list[i].freq, (int32_t)h_list[i].rune};
+    HuffTree tree;
+    huff_build_tree(leaves, tree);
+    std::vector<HuffCode> codes;
+    if (!huff_codes(tree, codes)) return RSN_ERR_UNSUPPORTED;  // a code longer than 64 bits
+    std::vector<uint8_t> hdr;
+    huff_header(leaves, hdr);
+    std::vector<CodeEntry> h_codes(codes.size());
+    uint64_t total_bits = 0;
+    {
+        std::vector<uint64_t> fr(kRuneSpace, 0);
+        for (const HuffLeaf &l : leaves) fr[l.rune] = (uint64_t)l.freq;
+        for (size_t i = 0; i < codes.size(); i++) {
+            h_codes[i] = CodeEntry{(uint32_t)codes[i].rune, codes[i].len, codes[i].code};
+            total_bits += (uint64_t)codes[i].len * fr[codes[i].rune];
+        }
+    }
+    const uint32_t pad = (uint32_t)((8 - total_bits % 8) % 8);  // huffman.go:245-249
+    const size_t payload = (size_t)((total_bits + pad) / 8);
+    const size_t prefix = hdr.size() + 3;  // header, 5C 0A, pad byte
+    const size_t total = prefix + payload;
+
+    // ---- device: code tables
+    DevBuf code_tab, len_tab, clist;
+    RSN_TRY(code_tab.alloc((size_t)kRuneSpace * 8, s));
+    RSN_TRY(len_tab.alloc((size_t)kRuneSpace, s));
+    RSN_TRY(clist.alloc(h_codes.size() * sizeof(CodeEntry) + 16, s));
+    RSN_CUDA(cudaMemcpyAsync(clist.p, h_codes.data(), h_codes.size() * sizeof(CodeEntry), cudaMemcpyHostToDevice, s));
+    RSN_LAUNCH(k_code_scatter, (unsigned)div_up(h_codes.size(), 256), 256, 0, s, clist.as<CodeEntry>(), h_codes.size(),
+               code_tab.as<uint64_t>(), len_tab.as<uint8_t>());
+
+    // ---- output buffer: zero, then header | 5C 0A | pad, then the bits
+    DevBuf out;
+    RSN_TRY(out.alloc(total + 16, s));
+    RSN_CUDA(cudaMemsetAsync(out.p, 0, total + 16, s));
+    std::vector<uint8_t> pre(hdr);
+    pre.push_back(0x5C);
+    pre.push_back(0x0A);
+    pre.push_back((uint8_t)pad);
+    RSN_CUDA(cudaMemcpyAsync(out.p, pre.data(), pre.size(), cudaMemcpyHostToDevice, s));
+    if (total_bits) {
+        DevBuf tb, tbo;
+        RSN_TRY(tb.alloc(tiles * 8, s));
+        RSN_TRY(tbo.alloc((tiles + 1) * 8, s));
+        RSN_LAUNCH(k_enc_count, (unsigned)tiles, kTileThreads, 0, s, d_in, n, len_tab.as<uint8_t>(), tb.as<uint64_t>());
+        RSN_TRY(spine_scan_u64(tb.as<uint64_t>(), tbo.as<uint64_t>(), tbo.as<uint64_t>() + tiles, tiles, s));
+        RSN_LAUNCH(k_enc_write, (unsigned)tiles, kTileThreads, 0, s, d_in, n, code_tab.as<uint64_t>(),
+                   len_tab.as<uint8_t>(), tbo.as<uint64_t>(), (uint64_t)prefix * 8 + pad, out.as<uint32_t>());
+    }
+    // h_codes / pre are read by async copies: wait before they go out of scope
+    RSN_CUDA(cudaStreamSynchronize(s));
+    (void)c;
+    *d_out = (uint8_t *)out.release();
+    *out_n = total;
+    return RSN_OK;
+}
+
+}  // namespace rsn

