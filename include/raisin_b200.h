@@ -102,6 +102,9 @@ int rsn_dev_huff_compress(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t
 int rsn_dev_huff_decompress(const uint8_t *d_in, size_t n, int strict_limits, uint8_t **d_out, size_t *out_n,
                             void *stream);
 void rsn_dev_free(void *d_ptr, void *stream);
+/* Convenience copies between host and device buffers on `stream` (synchronous on return). */
+int rsn_dev_download(const void *d_src, size_t n, void *h_dst, void *stream);
+int rsn_dev_upload(const void *h_src, size_t n, void *d_dst, void *stream);
 
 /*
  * Per-position match arrays of variant A over an already-escaped device buffer: for each i,

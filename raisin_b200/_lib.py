@@ -16,7 +16,8 @@ EXPORTS = [
     "rsn_init", "rsn_shutdown", "rsn_strerror", "rsn_last_cuda_error", "rsn_free", "rsn_host_alloc",
     "rsn_host_free", "rsn_lzss_compress", "rsn_lzss_decompress", "rsn_huff_compress", "rsn_huff_decompress",
     "rsn_compress_layers", "rsn_decompress_layers", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
-    "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_free", "rsn_dev_lzss_match",
+    "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_free", "rsn_dev_download", "rsn_dev_upload",
+    "rsn_dev_lzss_match",
     "rsn_kernel_launches", "rsn_reset_kernel_launches", "rsn_version",
 ]
 
@@ -74,10 +75,13 @@ def lib():
     L.rsn_dev_huff_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, vpp, szp, C.c_void_p]
     L.rsn_dev_free.argtypes = [C.c_void_p, C.c_void_p]
     L.rsn_dev_free.restype = None
+    L.rsn_dev_download.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.rsn_dev_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.rsn_dev_lzss_match.argtypes = [C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p]
     for name in ("rsn_lzss_compress", "rsn_lzss_decompress", "rsn_huff_compress", "rsn_huff_decompress",
                  "rsn_compress_layers", "rsn_decompress_layers", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
-                 "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_lzss_match"):
+                 "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_lzss_match", "rsn_dev_download",
+                 "rsn_dev_upload"):
         getattr(L, name).restype = C.c_int
     L.rsn_kernel_launches.argtypes = []
     L.rsn_kernel_launches.restype = C.c_uint64

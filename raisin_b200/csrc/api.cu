@@ -167,27 +167,51 @@ int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, u
 
 // ---- device-buffer API
 
+// stream == NULL: run on the context's own stream and synchronise before returning
+static int finish(int rc, void *stream) {
+    if (!stream) {
+        cudaError_t e = cudaStreamSynchronize(ctx().own_stream);
+        if (rc == RSN_OK && e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    return rc;
+}
+
 int rsn_dev_lzss_compress(const uint8_t *d_in, size_t n, int64_t window, int variant, uint8_t **d_out, size_t *out_n,
                           void *stream) {
     if ((!d_in && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());
-    return lzss_compress_dev(d_in, n, window, variant, d_out, out_n, pick_stream(stream));
+    return finish(lzss_compress_dev(d_in, n, window, variant, d_out, out_n, pick_stream(stream)), stream);
 }
 int rsn_dev_lzss_decompress(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, void *stream) {
     if ((!d_in && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());
-    return lzss_decompress_dev(d_in, n, d_out, out_n, pick_stream(stream));
+    return finish(lzss_decompress_dev(d_in, n, d_out, out_n, pick_stream(stream)), stream);
 }
 int rsn_dev_huff_compress(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, void *stream) {
     if ((!d_in && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());
-    return huff_compress_dev(d_in, n, d_out, out_n, pick_stream(stream));
+    return finish(huff_compress_dev(d_in, n, d_out, out_n, pick_stream(stream)), stream);
 }
 int rsn_dev_huff_decompress(const uint8_t *d_in, size_t n, int strict_limits, uint8_t **d_out, size_t *out_n,
                             void *stream) {
     if ((!d_in && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());
-    return huff_decompress_dev(d_in, n, nullptr, strict_limits, d_out, out_n, pick_stream(stream));
+    return finish(huff_decompress_dev(d_in, n, nullptr, strict_limits, d_out, out_n, pick_stream(stream)), stream);
+}
+
+int rsn_dev_download(const void *d_src, size_t n, void *h_dst, void *stream) {
+    RSN_TRY(ensure_ctx());
+    cudaStream_t s = pick_stream(stream);
+    if (n) RSN_CUDA(cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    return RSN_OK;
+}
+int rsn_dev_upload(const void *h_src, size_t n, void *d_dst, void *stream) {
+    RSN_TRY(ensure_ctx());
+    cudaStream_t s = pick_stream(stream);
+    if (n) RSN_CUDA(cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    return RSN_OK;
 }
 
 int rsn_dev_lzss_match(const uint8_t *d_enc, size_t n, int64_t window, uint32_t *d_packed, void *stream) {
@@ -196,7 +220,7 @@ int rsn_dev_lzss_match(const uint8_t *d_enc, size_t n, int64_t window, uint32_t 
     if (n == 0) return RSN_OK;
     uint32_t W = 0;
     RSN_TRY(lzss_effective_window(window, n, &W));
-    return lzss_match(d_enc, n, W, d_packed, pick_stream(stream));
+    return finish(lzss_match(d_enc, n, W, d_packed, pick_stream(stream)), stream);
 }
 
 }  // extern "C"
