@@ -299,6 +299,8 @@ int lzss_match(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, c
     if (n == 0) return RSN_OK;
     if (W < 1 || W > kMaxWindow) return RSN_ERR_INVALID_ARG;
     if (reinterpret_cast<uintptr_t>(d_enc) & 3) return RSN_ERR_INVALID_ARG;  // word loads
+    if (W <= 4096) return lzss_match_tile(d_enc, n, W, d_packed, s);  // shared-memory tile kernel
+    // wider windows: hash-chain path (global memory)
     const uint32_t *words = reinterpret_cast<const uint32_t *>(d_enc);
     const size_t nwords = (n + 3) / 4;
     if (n < 2048) {

@@ -1,0 +1,304 @@
+// lzss_match_tile.cu — K2 for windows up to 4096 (the engine's window, lzss.go:35): every
+// position's longest match from a tile staged in shared memory.
+//
+// One CTA owns T = 4096 consecutive positions plus a halo of W+2 earlier bytes and W bytes of
+// look-ahead, all staged in shared memory.  The positions e of halo+tile ("entries") are sorted
+// by their 3-gram (enc[e], enc[e+1], enc[e+2]) with a stable LSD radix sort, least significant
+// byte = enc[e+2] first.  Stability plus that digit order give, for free:
+//   after pass 1: entries grouped by enc[e+2], in position order  -> nearest earlier equal byte
+//                 of position q = e+2                              -> "L(q) >= 1"
+//   after pass 2: grouped by (enc[e+1], enc[e+2])                  -> "L(q) >= 2" for q = e+1
+//   after pass 3: grouped by the whole 3-gram, in position order   -> "L(q) >= 3" for q = e and
+//                 the complete, contiguous candidate list of every position for L >= 4.
+// A radix pass ranks 32 entries at a time with 8 warp ballots (peers with the same digit), per-warp
+// digit counters (no atomics) and one block scan.
+//
+// Candidates of a position are then evaluated far to near (the list is in position order), with
+// 4-byte unaligned shared-memory compares; the scan stops as soon as the remaining distances
+// cannot beat the best length, which also keeps degenerate inputs (runs, short periods) bounded:
+// L(i) = max_d min(lcp(i-d,i), d, n-i), ties to the larger d (leftmost source, lzss.go:166-184).
+#include "lzss.cuh"
+
+namespace rsn {
+
+namespace tile {
+
+constexpr int T = 4096;            // positions per CTA
+constexpr int WMAX = 4096;         // largest window handled here
+constexpr int EMAX = T + WMAX + 8; // entries: halo (W+2, rounded down to a word boundary) + tile
+constexpr int ECAP = EMAX + 30;    // rounded for warp chunks
+constexpr int SLEN = EMAX + WMAX + 16;
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+
+struct Smem {
+    uint32_t s_words[SLEN / 4 + 2];   // staged bytes: [base, base + stage_len)
+    uint16_t a[ECAP];                 // ping
+    uint16_t b[ECAP];                 // pong; after the sort the spare one holds the u32 results
+    uint16_t cnt[256 * WARPS];        // [digit][warp]
+    uint32_t heads[ECAP / 32 + 2];    // bit r: slot r starts a 3-gram group
+    uint8_t lowL[T];                  // 0..3 from the 1/2/3-gram stages
+    uint32_t scan[33];
+};
+
+__device__ __forceinline__ uint32_t lds32(const uint8_t *s, uint32_t pos) {
+    const uint32_t a = pos & ~3u;
+    const uint32_t lo = *reinterpret_cast<const uint32_t *>(s + a);
+    const uint32_t hi = *reinterpret_cast<const uint32_t *>(s + a + 4);
+    return __funnelshift_r(lo, hi, (pos & 3u) * 8);
+}
+
+// lanes with the same 8-bit digit as mine (among `active` lanes)
+__device__ __forceinline__ unsigned same_digit(uint32_t digit, unsigned active) {
+    unsigned peers = active;
+#pragma unroll
+    for (int bit = 0; bit < 8; bit++) {
+        const unsigned m = __ballot_sync(0xffffffffu, (digit >> bit) & 1u);
+        peers &= ((digit >> bit) & 1u) ? m : ~m;
+    }
+    return peers;
+}
+
+// One stable counting pass on byte s[e + byteoff] from src to dst over slots [0, ev).
+__device__ __forceinline__ void radix_pass(Smem &sm, const uint8_t *s, const uint16_t *src, uint16_t *dst,
+                                           uint32_t ev, uint32_t byteoff) {
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t per = ((ev + WARPS - 1) / WARPS + 31) & ~31u;  // slots per warp, multiple of 32
+    const uint32_t lo = min(ev, w * per), hi = min(ev, lo + per);
+    for (int i = threadIdx.x; i < 256 * WARPS; i += THREADS) sm.cnt[i] = 0;
+    __syncthreads();
+    // count
+    for (uint32_t c = lo; c < hi; c += 32) {
+        const uint32_t slot = c + lane;
+        const bool act = slot < hi;
+        const uint32_t e = act ? src[slot] : 0;
+        const uint32_t digit = act ? s[e + byteoff] : 0;
+        const unsigned active = __ballot_sync(0xffffffffu, act);
+        const unsigned peers = same_digit(digit, active);
+        if (act && (peers & ((1u << lane) - 1)) == 0)  // lowest lane of each digit group
+            sm.cnt[digit * WARPS + w] += (uint16_t)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan of cnt in (digit, warp) order: 256*WARPS values, 8 per thread
+    {
+        uint32_t v[WARPS];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < WARPS; k++) {
+            v[k] = sm.cnt[threadIdx.x * WARPS + k];
+            sum += v[k];
+        }
+        uint32_t total;
+        uint32_t run = block_exclusive_sum<uint32_t>(sum, sm.scan, total);
+#pragma unroll
+        for (int k = 0; k < WARPS; k++) {
+            sm.cnt[threadIdx.x * WARPS + k] = (uint16_t)run;
+            run += v[k];
+        }
+    }
+    __syncthreads();
+    // scatter
+    for (uint32_t c = lo; c < hi; c += 32) {
+        const uint32_t slot = c + lane;
+        const bool act = slot < hi;
+        const uint32_t e = act ? src[slot] : 0;
+        const uint32_t digit = act ? s[e + byteoff] : 0;
+        const unsigned active = __ballot_sync(0xffffffffu, act);
+        const unsigned peers = same_digit(digit, active);
+        uint32_t basev = 0;
+        if (act) basev = sm.cnt[digit * WARPS + w];
+        __syncwarp();
+        if (act) {
+            dst[basev + __popc(peers & ((1u << lane) - 1))] = (uint16_t)e;
+            if ((peers >> lane) == 1u) sm.cnt[digit * WARPS + w] = (uint16_t)(basev + __popc(peers));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+}  // namespace tile
+
+__global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
+                                                              uint32_t *__restrict__ packed) {
+    using namespace tile;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    uint8_t *s = reinterpret_cast<uint8_t *>(sm.s_words);
+
+    const size_t tile_start = (size_t)blockIdx.x * T;
+    const uint32_t tile_len = (uint32_t)min((size_t)T, n - tile_start);
+    const size_t base = tile_start > (size_t)W + 2 ? ((tile_start - W - 2) & ~(size_t)3) : 0;  // word aligned
+    const uint32_t halo = (uint32_t)(tile_start - base);
+    const uint32_t avail = (uint32_t)min(n - base, (size_t)(halo + T + W));  // bytes staged
+    // entries: positions with a complete 3-gram, up to the end of the tile
+    const uint32_t ev = avail >= 3 ? min(halo + tile_len, avail - 2) : 0;
+
+    // ---- stage bytes (zero padded), identity order, clear flags
+    {
+        const uint32_t nwords = (avail + 3) / 4;
+        const uint8_t *g = enc + base;
+        if ((reinterpret_cast<uintptr_t>(g) & 3) == 0) {
+            const uint32_t *gw = reinterpret_cast<const uint32_t *>(g);
+            const uint32_t full = avail / 4;
+            for (uint32_t i = threadIdx.x; i < full; i += THREADS) sm.s_words[i] = __ldg(gw + i);
+            if (threadIdx.x == 0 && full < nwords) {
+                uint32_t v = 0;
+                for (uint32_t b = full * 4; b < avail; b++) v |= (uint32_t)__ldg(g + b) << ((b & 3) * 8);
+                sm.s_words[full] = v;
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < nwords; i += THREADS) {
+                uint32_t v = 0;
+                for (uint32_t b = 0; b < 4; b++)
+                    if (i * 4 + b < avail) v |= (uint32_t)__ldg(g + i * 4 + b) << (b * 8);
+                sm.s_words[i] = v;
+            }
+        }
+        for (uint32_t i = nwords + threadIdx.x; i < nwords + 4 && i < SLEN / 4 + 2; i += THREADS) sm.s_words[i] = 0;
+        for (uint32_t e = threadIdx.x; e < ev; e += THREADS) sm.a[e] = (uint16_t)e;
+        for (uint32_t i = threadIdx.x; i < T; i += THREADS) sm.lowL[i] = 0;
+    }
+    __syncthreads();
+
+    // ---- pass 1: by enc[e+2]  ->  1-byte matches of q = e+2
+    radix_pass(sm, s, sm.a, sm.b, ev, 2);
+    for (uint32_t r = threadIdx.x; r < ev; r += THREADS) {
+        const uint32_t e = sm.b[r], q = e + 2;
+        if (q >= halo && q < halo + tile_len && r > 0) {
+            const uint32_t p = sm.b[r - 1];
+            if (s[p + 2] == s[q] && e - p <= W) sm.lowL[q - halo] = 1;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: by (enc[e+1], enc[e+2])  ->  2-byte matches of q = e+1 at distance >= 2
+    radix_pass(sm, s, sm.b, sm.a, ev, 1);
+    for (uint32_t r = threadIdx.x; r < ev; r += THREADS) {
+        const uint32_t e = sm.a[r], q = e + 1;
+        if (q >= halo && q < halo + tile_len) {
+            const uint32_t key = lds32(s, q) & 0xFFFFu;
+            bool hit = false;
+            for (uint32_t k = 1; k <= 2 && k <= r; k++) {
+                const uint32_t p = sm.a[r - k];
+                if ((lds32(s, p + 1) & 0xFFFFu) != key) break;
+                const uint32_t d = e - p;
+                if (d >= 2) {
+                    hit = d <= W;
+                    break;
+                }
+            }
+            if (hit) sm.lowL[q - halo] = 2;
+        }
+    }
+    __syncthreads();
+    // ---- pass 3: by the 3-gram  ->  3-byte matches of q = e at distance >= 3, and candidate lists
+    radix_pass(sm, s, sm.a, sm.b, ev, 0);
+    const uint16_t *arr = sm.b;                      // sorted by (3-gram, position)
+    // group heads
+    for (uint32_t r0 = (threadIdx.x >> 5) * 32; r0 < ev; r0 += THREADS) {
+        const uint32_t r = r0 + (threadIdx.x & 31);
+        bool head = false;
+        if (r < ev) head = r == 0 || ((lds32(s, arr[r]) ^ lds32(s, arr[r - 1])) & 0xFFFFFFu) != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, head);
+        if ((threadIdx.x & 31) == 0) sm.heads[r0 >> 5] = m;
+    }
+    __syncthreads();
+
+    // ---- candidates, far to near; one thread per sorted slot
+    // results go straight to global memory through `packed`; positions without an entry (the last
+    // two of the stream) and positions that only have short matches take lowL.
+    for (uint32_t r = threadIdx.x; r < ((ev + 31) & ~31u); r += THREADS) {
+        if (r >= ev) continue;
+        const uint32_t e = arr[r];
+        if (e < halo) continue;  // halo entries are candidates only
+        const uint32_t room = (uint32_t)min((size_t)W, n - (base + e));
+        // start of my group: highest head bit at or below r
+        uint32_t wi = r >> 5;
+        uint32_t bits = sm.heads[wi] & (0xFFFFFFFFu >> (31 - (r & 31)));
+        while (bits == 0) bits = sm.heads[--wi];
+        const uint32_t gs = (wi << 5) + (31 - __clz(bits));
+        // first candidate inside the window: lowest slot in [gs, r) with position >= e - W
+        uint32_t lo = gs, hi = r;
+        if (e > W) {
+            const uint32_t minpos = e - W;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (arr[mid] < minpos) lo = mid + 1;
+                else hi = mid;
+            }
+        }
+        uint32_t best = 3, boff = 0;  // looking for > 3; the 3-gram itself matches for every candidate
+        // arr[lo] is the farthest candidate: a 3-byte match exists iff its distance is >= 3
+        const bool has3 = lo < r && e - arr[lo] >= 3;
+        for (uint32_t c = lo; c < r; c++) {
+            const uint32_t j = arr[c];
+            const uint32_t d = e - j;
+            const uint32_t cap = min(d, room);
+            if (cap <= best) break;  // nearer candidates yield even less
+            if (s[j + best] != s[e + best]) continue;  // must beat `best`
+            uint32_t l = 3;
+            while (l < cap) {
+                const uint32_t x = lds32(s, j + l) ^ lds32(s, e + l);
+                if (x) {
+                    l += (__ffs(x) - 1) >> 3;
+                    break;
+                }
+                l += 4;
+            }
+            l = min(l, cap);
+            if (l > best) {
+                best = l;
+                boff = d;
+            }
+        }
+        uint32_t L, off = 0;
+        if (best >= 4) {
+            L = best;
+            off = boff;
+        } else if (has3 && room >= 3) {
+            L = 3;
+        } else {
+            L = sm.lowL[e - halo];
+        }
+        sm.lowL[e - halo] = 0xFF;  // mark as written
+        packed[base + e] = (L << 16) | off;
+    }
+    __syncthreads();
+    // positions of the tile that have no entry (no complete 3-gram: the last two of the stream)
+    for (uint32_t x = threadIdx.x; x < tile_len; x += THREADS) {
+        const uint8_t v = sm.lowL[x];
+        if (v != 0xFF) packed[tile_start + x] = (uint32_t)v << 16;
+    }
+}
+
+// Tile 0 has no halo, so stream positions 0 and 1 never appear as the third byte of an entry and
+// position 0 never as the second: add the 1- and 2-byte matches whose source starts there.
+__global__ void k_match_tile_fix0(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
+                                  uint32_t *__restrict__ packed) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n || q > (size_t)W + 1) return;
+    uint32_t L = packed[q] >> 16;
+    if (L >= 3) return;
+    uint32_t want = L;
+    // 2-gram at source 0 (distance q >= 2, q <= W)
+    if (q >= 2 && q <= W && q + 2 <= n && enc[0] == enc[q] && enc[1] == enc[q + 1]) want = max(want, 2u);
+    // single byte at source 0 (distance q) or 1 (distance q-1)
+    if (q >= 1 && q <= W && enc[0] == enc[q]) want = max(want, 1u);
+    if (q >= 2 && q - 1 <= W && enc[1] == enc[q]) want = max(want, 1u);
+    if (want != L) packed[q] = want << 16;
+}
+
+int lzss_match_tile(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, cudaStream_t s) {
+    static thread_local bool attr_set = false;
+    const size_t smem = sizeof(tile::Smem);
+    if (!attr_set) {
+        RSN_CUDA(cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    RSN_LAUNCH(k_match_tile, (unsigned)div_up(n, tile::T), tile::THREADS, smem, s, d_enc, n, W, d_packed);
+    RSN_LAUNCH(k_match_tile_fix0, (unsigned)div_up(min(n, (size_t)W + 2), 128), 128, 0, s, d_enc, n, W, d_packed);
+    return RSN_OK;
+}
+
+}  // namespace rsn
