@@ -1,7 +1,7 @@
 // lzss_match_tile.cu — K2 for windows up to 4096 (the engine's window, lzss.go:35): every
 // position's longest match from a tile staged in shared memory.
 //
-// One CTA owns T = 4096 consecutive positions plus a halo of W+2 earlier bytes and W bytes of
+// One CTA owns T = 8192 consecutive positions plus a halo of W+2 earlier bytes and W bytes of
 // look-ahead, all staged in shared memory.  The positions e of halo+tile ("entries") are sorted
 // by their 3-gram (enc[e], enc[e+1], enc[e+2]) with a stable LSD radix sort, least significant
 // byte = enc[e+2] first.  Stability plus that digit order give, for free:
@@ -23,22 +23,24 @@ namespace rsn {
 
 namespace tile {
 
-constexpr int T = 4096;            // positions per CTA
-constexpr int WMAX = 4096;         // largest window handled here
-constexpr int EMAX = T + WMAX + 8; // entries: halo (W+2, rounded down to a word boundary) + tile
-constexpr int ECAP = EMAX + 30;    // rounded for warp chunks
-constexpr int SLEN = EMAX + WMAX + 16;
-constexpr int THREADS = 256;
+constexpr int T = 8192;             // positions per CTA
+constexpr int WMAX = 4096;          // largest window handled here
+constexpr int EMAX = T + WMAX + 24; // entries: halo (W+2, rounded down to 16 bytes) + tile
+constexpr int ECAP = EMAX + 40;     // rounded for warp chunks
+constexpr int SLEN = EMAX + WMAX + 32;
+constexpr int THREADS = 512;
 constexpr int WARPS = THREADS / 32;
 
 struct Smem {
-    uint32_t s_words[SLEN / 4 + 2];   // staged bytes: [base, base + stage_len)
+    uint32_t s_words[SLEN / 4 + 4];   // staged bytes: [base, base + avail), zero padded
     uint16_t a[ECAP];                 // ping
-    uint16_t b[ECAP];                 // pong; after the sort the spare one holds the u32 results
+    uint16_t b[ECAP];                 // pong
     uint16_t cnt[256 * WARPS];        // [digit][warp]
     uint32_t heads[ECAP / 32 + 2];    // bit r: slot r starts a 3-gram group
-    uint8_t lowL[T];                  // 0..3 from the 1/2/3-gram stages
+    uint8_t info[ECAP];               // per slot: rank inside its (chunk, digit) group | 0x80 if last of it
+    uint8_t lowL[T];                  // 0..3 from the 1/2/3-gram stages, 0xFF once the final result is written
     uint32_t scan[33];
+    uint32_t wtot[WARPS + 1];
 };
 
 __device__ __forceinline__ uint32_t lds32(const uint8_t *s, uint32_t pos) {
@@ -60,14 +62,17 @@ __device__ __forceinline__ unsigned same_digit(uint32_t digit, unsigned active) 
 }
 
 // One stable counting pass on byte s[e + byteoff] from src to dst over slots [0, ev).
+// Warp w owns the contiguous slots [w*per, (w+1)*per): counters are (digit, warp) so the exclusive
+// scan in that order yields stable destinations without atomics.
 __device__ __forceinline__ void radix_pass(Smem &sm, const uint8_t *s, const uint16_t *src, uint16_t *dst,
                                            uint32_t ev, uint32_t byteoff) {
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1;
     const uint32_t per = ((ev + WARPS - 1) / WARPS + 31) & ~31u;  // slots per warp, multiple of 32
     const uint32_t lo = min(ev, w * per), hi = min(ev, lo + per);
     for (int i = threadIdx.x; i < 256 * WARPS; i += THREADS) sm.cnt[i] = 0;
     __syncthreads();
-    // count
+    // count (and remember each slot's rank inside its 32-slot digit group)
     for (uint32_t c = lo; c < hi; c += 32) {
         const uint32_t slot = c + lane;
         const bool act = slot < hi;
@@ -75,25 +80,30 @@ __device__ __forceinline__ void radix_pass(Smem &sm, const uint8_t *s, const uin
         const uint32_t digit = act ? s[e + byteoff] : 0;
         const unsigned active = __ballot_sync(0xffffffffu, act);
         const unsigned peers = same_digit(digit, active);
-        if (act && (peers & ((1u << lane) - 1)) == 0)  // lowest lane of each digit group
-            sm.cnt[digit * WARPS + w] += (uint16_t)__popc(peers);
+        if (act) {
+            const uint32_t rank = __popc(peers & lt);
+            const bool last = (peers >> lane) == 1u;
+            sm.info[slot] = (uint8_t)(rank | (last ? 0x80u : 0u));
+            if (last) sm.cnt[digit * WARPS + w] += (uint16_t)(rank + 1);
+        }
         __syncwarp();
     }
     __syncthreads();
     // exclusive scan of cnt in (digit, warp) order: 256*WARPS values, 8 per thread
     {
-        uint32_t v[WARPS];
+        constexpr int PER = 256 * WARPS / THREADS;
+        uint32_t v[PER];
         uint32_t sum = 0;
 #pragma unroll
-        for (int k = 0; k < WARPS; k++) {
-            v[k] = sm.cnt[threadIdx.x * WARPS + k];
+        for (int k = 0; k < PER; k++) {
+            v[k] = sm.cnt[threadIdx.x * PER + k];
             sum += v[k];
         }
         uint32_t total;
         uint32_t run = block_exclusive_sum<uint32_t>(sum, sm.scan, total);
 #pragma unroll
-        for (int k = 0; k < WARPS; k++) {
-            sm.cnt[threadIdx.x * WARPS + k] = (uint16_t)run;
+        for (int k = 0; k < PER; k++) {
+            sm.cnt[threadIdx.x * PER + k] = (uint16_t)run;
             run += v[k];
         }
     }
@@ -102,16 +112,18 @@ __device__ __forceinline__ void radix_pass(Smem &sm, const uint8_t *s, const uin
     for (uint32_t c = lo; c < hi; c += 32) {
         const uint32_t slot = c + lane;
         const bool act = slot < hi;
-        const uint32_t e = act ? src[slot] : 0;
-        const uint32_t digit = act ? s[e + byteoff] : 0;
-        const unsigned active = __ballot_sync(0xffffffffu, act);
-        const unsigned peers = same_digit(digit, active);
-        uint32_t basev = 0;
-        if (act) basev = sm.cnt[digit * WARPS + w];
+        uint32_t e = 0, digit = 0, inf = 0, basev = 0;
+        if (act) {
+            e = src[slot];
+            digit = s[e + byteoff];
+            inf = sm.info[slot];
+            basev = sm.cnt[digit * WARPS + w];
+        }
         __syncwarp();
         if (act) {
-            dst[basev + __popc(peers & ((1u << lane) - 1))] = (uint16_t)e;
-            if ((peers >> lane) == 1u) sm.cnt[digit * WARPS + w] = (uint16_t)(basev + __popc(peers));
+            const uint32_t rank = inf & 0x7Fu;
+            dst[basev + rank] = (uint16_t)e;
+            if (inf & 0x80u) sm.cnt[digit * WARPS + w] = (uint16_t)(basev + rank + 1);
         }
         __syncwarp();
     }
@@ -126,10 +138,11 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     uint8_t *s = reinterpret_cast<uint8_t *>(sm.s_words);
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
     const size_t tile_start = (size_t)blockIdx.x * T;
     const uint32_t tile_len = (uint32_t)min((size_t)T, n - tile_start);
-    const size_t base = tile_start > (size_t)W + 2 ? ((tile_start - W - 2) & ~(size_t)3) : 0;  // word aligned
+    const size_t base = tile_start > (size_t)W + 2 ? ((tile_start - W - 2) & ~(size_t)15) : 0;  // 16-byte aligned
     const uint32_t halo = (uint32_t)(tile_start - base);
     const uint32_t avail = (uint32_t)min(n - base, (size_t)(halo + T + W));  // bytes staged
     // entries: positions with a complete 3-gram, up to the end of the tile
@@ -139,14 +152,16 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
     {
         const uint32_t nwords = (avail + 3) / 4;
         const uint8_t *g = enc + base;
-        if ((reinterpret_cast<uintptr_t>(g) & 3) == 0) {
-            const uint32_t *gw = reinterpret_cast<const uint32_t *>(g);
-            const uint32_t full = avail / 4;
-            for (uint32_t i = threadIdx.x; i < full; i += THREADS) sm.s_words[i] = __ldg(gw + i);
-            if (threadIdx.x == 0 && full < nwords) {
+        if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+            const uint4 *gv = reinterpret_cast<const uint4 *>(g);
+            uint4 *sv = reinterpret_cast<uint4 *>(sm.s_words);
+            const uint32_t fullv = avail / 16;
+            for (uint32_t i = threadIdx.x; i < fullv; i += THREADS) sv[i] = __ldg(gv + i);
+            for (uint32_t i = fullv * 4 + threadIdx.x; i < nwords; i += THREADS) {
                 uint32_t v = 0;
-                for (uint32_t b = full * 4; b < avail; b++) v |= (uint32_t)__ldg(g + b) << ((b & 3) * 8);
-                sm.s_words[full] = v;
+                for (uint32_t b = 0; b < 4; b++)
+                    if (i * 4 + b < avail) v |= (uint32_t)__ldg(g + i * 4 + b) << (b * 8);
+                sm.s_words[i] = v;
             }
         } else {
             for (uint32_t i = threadIdx.x; i < nwords; i += THREADS) {
@@ -156,7 +171,7 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
                 sm.s_words[i] = v;
             }
         }
-        for (uint32_t i = nwords + threadIdx.x; i < nwords + 4 && i < SLEN / 4 + 2; i += THREADS) sm.s_words[i] = 0;
+        for (uint32_t i = nwords + threadIdx.x; i < nwords + 4 && i < SLEN / 4 + 4; i += THREADS) sm.s_words[i] = 0;
         for (uint32_t e = threadIdx.x; e < ev; e += THREADS) sm.a[e] = (uint16_t)e;
         for (uint32_t i = threadIdx.x; i < T; i += THREADS) sm.lowL[i] = 0;
     }
@@ -192,77 +207,142 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
         }
     }
     __syncthreads();
-    // ---- pass 3: by the 3-gram  ->  3-byte matches of q = e at distance >= 3, and candidate lists
+    // ---- pass 3: by the 3-gram  ->  candidate lists in position order
     radix_pass(sm, s, sm.a, sm.b, ev, 0);
-    const uint16_t *arr = sm.b;                      // sorted by (3-gram, position)
-    // group heads
-    for (uint32_t r0 = (threadIdx.x >> 5) * 32; r0 < ev; r0 += THREADS) {
-        const uint32_t r = r0 + (threadIdx.x & 31);
-        bool head = false;
-        if (r < ev) head = r == 0 || ((lds32(s, arr[r]) ^ lds32(s, arr[r - 1])) & 0xFFFFFFu) != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, head);
-        if ((threadIdx.x & 31) == 0) sm.heads[r0 >> 5] = m;
+    const uint16_t *arr = sm.b;  // sorted by (3-gram, position)
+    uint16_t *list = sm.a;       // spare buffer: the sorted slots that belong to the tile, compacted
+    // group heads + per-warp count of tile slots
+    {
+        const uint32_t per = ((ev + WARPS - 1) / WARPS + 31) & ~31u;
+        const uint32_t lo = min(ev, w * per), hi = min(ev, lo + per);
+        uint32_t mine = 0;
+        for (uint32_t c = lo; c < hi; c += 32) {
+            const uint32_t r = c + lane;
+            bool head = false, in_tile = false;
+            if (r < hi) {
+                const uint32_t e = arr[r];
+                head = r == 0 || ((lds32(s, e) ^ lds32(s, arr[r - 1])) & 0xFFFFFFu) != 0;
+                in_tile = e >= halo;
+            }
+            const unsigned hm = __ballot_sync(0xffffffffu, head);
+            const unsigned tm = __ballot_sync(0xffffffffu, in_tile);
+            if (lane == 0) sm.heads[c >> 5] = hm;
+            mine += __popc(tm);
+        }
+        if (lane == 0) sm.wtot[w] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (int k = 0; k < WARPS; k++) {
+                const uint32_t v = sm.wtot[k];
+                sm.wtot[k] = run;
+                run += v;
+            }
+            sm.wtot[WARPS] = run;
+        }
+        __syncthreads();
+        uint32_t out = sm.wtot[w];
+        for (uint32_t c = lo; c < hi; c += 32) {
+            const uint32_t r = c + lane;
+            const bool in_tile = r < hi && arr[r] >= halo;
+            const unsigned tm = __ballot_sync(0xffffffffu, in_tile);
+            if (in_tile) list[out + __popc(tm & ((1u << lane) - 1))] = (uint16_t)r;
+            out += __popc(tm);
+        }
     }
     __syncthreads();
+    const uint32_t n_list = sm.wtot[WARPS];
 
-    // ---- candidates, far to near; one thread per sorted slot
-    // results go straight to global memory through `packed`; positions without an entry (the last
-    // two of the stream) and positions that only have short matches take lowL.
-    for (uint32_t r = threadIdx.x; r < ((ev + 31) & ~31u); r += THREADS) {
-        if (r >= ev) continue;
-        const uint32_t e = arr[r];
-        if (e < halo) continue;  // halo entries are candidates only
-        const uint32_t room = (uint32_t)min((size_t)W, n - (base + e));
-        // start of my group: highest head bit at or below r
-        uint32_t wi = r >> 5;
-        uint32_t bits = sm.heads[wi] & (0xFFFFFFFFu >> (31 - (r & 31)));
-        while (bits == 0) bits = sm.heads[--wi];
-        const uint32_t gs = (wi << 5) + (31 - __clz(bits));
-        // first candidate inside the window: lowest slot in [gs, r) with position >= e - W
-        uint32_t lo = gs, hi = r;
-        if (e > W) {
-            const uint32_t minpos = e - W;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (arr[mid] < minpos) lo = mid + 1;
-                else hi = mid;
+    // ---- candidates, far to near; one thread per tile slot, in sorted order (neighbouring lanes
+    // sit in the same 3-gram group, so their candidate counts are similar)
+    for (uint32_t k0 = w * 32; k0 < n_list; k0 += THREADS) {
+        const uint32_t k = k0 + lane;
+        const bool act = k < n_list;
+        uint32_t r = 0, e = 0, room = 0, c = 0, best = 3, boff = 0;
+        bool has3 = false;
+        if (act) {
+            r = list[k];
+            e = arr[r];
+            room = (uint32_t)min((size_t)W, n - (base + e));
+            // start of my group: highest head bit at or below r
+            uint32_t wi = r >> 5;
+            uint32_t bits = sm.heads[wi] & (0xFFFFFFFFu >> (31 - (r & 31)));
+            while (bits == 0) bits = sm.heads[--wi];
+            uint32_t lo = (wi << 5) + (31 - __clz(bits)), hi = r;
+            // first candidate inside the window: lowest slot in [group start, r) with position >= e - W
+            if (e > W && lo < hi && arr[lo] < e - W) {
+                const uint32_t minpos = e - W;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (arr[mid] < minpos) lo = mid + 1;
+                    else hi = mid;
+                }
             }
+            c = lo;
+            // arr[lo] is the farthest candidate: a 3-byte match exists iff its distance is >= 3
+            has3 = lo < r && e - arr[lo] >= 3;
         }
-        uint32_t best = 3, boff = 0;  // looking for > 3; the 3-gram itself matches for every candidate
-        // arr[lo] is the farthest candidate: a 3-byte match exists iff its distance is >= 3
-        const bool has3 = lo < r && e - arr[lo] >= 3;
-        for (uint32_t c = lo; c < r; c++) {
-            const uint32_t j = arr[c];
-            const uint32_t d = e - j;
-            const uint32_t cap = min(d, room);
-            if (cap <= best) break;  // nearer candidates yield even less
-            if (s[j + best] != s[e + best]) continue;  // must beat `best`
-            uint32_t l = 3;
-            while (l < cap) {
-                const uint32_t x = lds32(s, j + l) ^ lds32(s, e + l);
-                if (x) {
-                    l += (__ffs(x) - 1) >> 3;
+        // Each round: every lane skips ahead to its next candidate that can still beat `best`
+        // (cheap, divergent), then all such lanes extend their match together.
+        // Invariants of the skip loop: a candidate at distance d yields at most min(d, room), so
+        // only slots with arr[c] < jlim = e - best can win (the list is in position order), and a
+        // winner must match the byte at offset `best` (tgt).
+        uint32_t jlim = e - best;            // candidates at j >= jlim have d <= best
+        if (room <= best) c = r;             // nothing can be longer than `room`
+        const uint8_t *sb = s + best;
+        uint32_t tgt = act ? s[e + best] : 0;
+        for (;;) {
+            uint32_t j = 0;
+            bool pend = false;
+            while (c < r) {
+                j = arr[c];
+                if (j >= jlim) {  // nearer candidates yield even less
+                    c = r;
                     break;
                 }
-                l += 4;
+                if (sb[j] == tgt) {
+                    pend = true;
+                    break;
+                }
+                c++;
             }
-            l = min(l, cap);
-            if (l > best) {
-                best = l;
-                boff = d;
+            if (!__any_sync(0xffffffffu, pend)) break;
+            if (pend) {
+                const uint32_t cap = min(e - j, room);
+                uint32_t l = 3;
+                while (l < cap) {
+                    const uint32_t x = lds32(s, j + l) ^ lds32(s, e + l);
+                    if (x) {
+                        l += (__ffs(x) - 1) >> 3;
+                        break;
+                    }
+                    l += 4;
+                }
+                l = min(l, cap);
+                if (l > best) {
+                    best = l;
+                    boff = e - j;
+                    jlim = e - best;
+                    sb = s + best;
+                    tgt = s[e + best];
+                    if (room <= best) c = r;
+                }
+                c++;
             }
         }
-        uint32_t L, off = 0;
-        if (best >= 4) {
-            L = best;
-            off = boff;
-        } else if (has3 && room >= 3) {
-            L = 3;
-        } else {
-            L = sm.lowL[e - halo];
+        if (act) {
+            uint32_t L, off = 0;
+            if (best >= 4) {
+                L = best;
+                off = boff;
+            } else if (has3 && room >= 3) {
+                L = 3;
+            } else {
+                L = sm.lowL[e - halo];
+            }
+            sm.lowL[e - halo] = 0xFF;  // final result written
+            packed[base + e] = (L << 16) | off;
         }
-        sm.lowL[e - halo] = 0xFF;  // mark as written
-        packed[base + e] = (L << 16) | off;
     }
     __syncthreads();
     // positions of the tile that have no entry (no complete 3-gram: the last two of the stream)
