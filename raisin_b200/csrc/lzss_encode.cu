@@ -16,21 +16,27 @@ namespace rsn {
 
 __device__ __forceinline__ bool is_special(uint8_t v) { return v == 0x5C || v == 0xFF; }
 
+// tile_cnt[t] = escaped size of tile t; *touched != 0 iff some byte changes ('<', 0x5C or 0xFF)
 __global__ void __launch_bounds__(kTileThreads) k_escape_count(const uint8_t *__restrict__ in, size_t n,
-                                                               uint64_t *__restrict__ tile_cnt) {
+                                                               uint64_t *__restrict__ tile_cnt,
+                                                               uint32_t *__restrict__ touched) {
     __shared__ uint32_t sm[33];
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
-    uint32_t cnt = 0;
+    uint32_t cnt = 0, changes = 0;
     if (base < n) {
         uint8_t v[16];
         load16(in, base, n, 0, v);
         const int valid = (int)min((size_t)16, n - base);
 #pragma unroll
-        for (int k = 0; k < 16; k++) cnt += (k < valid) ? 1u + (is_special(v[k]) ? 1u : 0u) : 0u;
+        for (int k = 0; k < 16; k++) {
+            cnt += (k < valid) ? 1u + (is_special(v[k]) ? 1u : 0u) : 0u;
+            changes += (k < valid && (is_special(v[k]) || v[k] == 0x3C)) ? 1u : 0u;
+        }
     }
     uint32_t total;
     block_exclusive_sum<uint32_t>(cnt, sm, total);
     if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+    if (__syncthreads_or(changes != 0) && threadIdx.x == 0) *touched = 1;
 }
 
 __global__ void __launch_bounds__(kTileThreads) k_escape_apply(const uint8_t *__restrict__ in, size_t n,
@@ -67,75 +73,139 @@ __global__ void __launch_bounds__(kTileThreads) k_escape_apply(const uint8_t *__
     for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = stage[i];
 }
 
-int lzss_escape(const uint8_t *d_in, size_t n, DevBuf &enc, size_t *enc_n, cudaStream_t s) {
+// On return *enc_ptr is the escaped buffer: either `enc` (owned) or d_in itself when no byte of
+// the input needs escaping or remapping (then nothing is copied).
+int lzss_escape(const uint8_t *d_in, size_t n, DevBuf &enc, const uint8_t **enc_ptr, size_t *enc_n, cudaStream_t s) {
+    *enc_ptr = d_in;
     if (n == 0) {
-        RSN_TRY(enc.alloc(16, s));
         *enc_n = 0;
         return RSN_OK;
     }
     const size_t tiles = div_up(n, kTile);
     DevBuf cnt, off;
     RSN_TRY(cnt.alloc(tiles * 8, s));
-    RSN_TRY(off.alloc((tiles + 1) * 8, s));
-    RSN_LAUNCH(k_escape_count, (unsigned)tiles, kTileThreads, 0, s, d_in, n, cnt.as<uint64_t>());
+    RSN_TRY(off.alloc((tiles + 2) * 8, s));
+    uint32_t *touched = reinterpret_cast<uint32_t *>(off.as<uint64_t>() + tiles + 1);
+    RSN_CUDA(cudaMemsetAsync(touched, 0, 8, s));
+    RSN_LAUNCH(k_escape_count, (unsigned)tiles, kTileThreads, 0, s, d_in, n, cnt.as<uint64_t>(), touched);
     RSN_TRY(spine_scan_u64(cnt.as<uint64_t>(), off.as<uint64_t>(), off.as<uint64_t>() + tiles, tiles, s));
-    uint64_t total = 0;
-    RSN_TRY(read_u64(off.as<uint64_t>() + tiles, &total, s));
+    Ctx &c = ctx();
+    RSN_CUDA(cudaMemcpyAsync(c.h_scalars, off.as<uint64_t>() + tiles, 16, cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    const uint64_t total = c.h_scalars[0];
+    if ((uint32_t)c.h_scalars[1] == 0 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0) {
+        *enc_n = n;  // identity: use the input in place
+        return RSN_OK;
+    }
     RSN_TRY(enc.alloc(total + 64, s));
+    *enc_ptr = enc.as<uint8_t>();
     RSN_LAUNCH(k_escape_apply, (unsigned)tiles, kTileThreads, 0, s, d_in, n, off.as<uint64_t>(), enc.as<uint8_t>());
     *enc_n = (size_t)total;
     return RSN_OK;
 }
 
 // ============================================================================= K3 parse
+//
+// The reference's merge loop (lzss.go:134-151) visits position 0, then i + max(L(i),1), ...; the
+// iterative variant (lzss.go:240-296) visits p, then p + 1 (no match may start at p) or
+// p + max(L,1) + 1 (the byte that ends a match is always a literal).  Either way the visited set
+// is the orbit of 0 under a per-position jump that only looks forward by at most J bytes.
+//   k_parse_exits   per 4096-position block, pointer doubling in shared memory: for EVERY position
+//                   of the block, the first orbit position at or beyond the block end (u16, relative)
+//   k_parse_up/top/down   a 64-ary hierarchy of such exit tables gives every block's true entry
+//   k_emit_plan     per block: synchronous doubling again, this time scattering a "visited" mark
+//                   from the block's entry (after round r the first 2^(r+1) orbit points are marked);
+//                   stores the visited bitmap and the block's output size
+//   k_emit_write    per block: token sizes -> block scan -> tokens staged in shared memory ->
+//                   coalesced copy to the output
 
-constexpr int kPB = 4096;   // parse block (positions)
-constexpr int kPS = 64;     // sub-block handled by one thread
-constexpr int kPT = kPB / kPS;  // 64 threads per CTA
-constexpr int kFan = 64;    // hierarchy fan-out
-static_assert(kPT == kPS, "k_parse_exits composes one sub-block per step with one thread per element");
+constexpr int kPB = 4096;        // parse block (positions)
+constexpr int kPT = 256;         // threads per CTA
+constexpr int kPI = kPB / kPT;   // 16 consecutive positions per thread
+constexpr int kFan = 64;         // hierarchy fan-out
 
-// jump[p] = max(L,1) for the block's positions into shared memory; positions >= n get 1.
-__device__ __forceinline__ void load_jumps(const uint32_t *__restrict__ lo, size_t start, size_t n, uint16_t *jump) {
-    for (int p = threadIdx.x; p < kPB; p += blockDim.x) {
-        const size_t g = start + p;
-        uint32_t L = g < n ? (__ldg(lo + g) >> 16) : 1u;
-        jump[p] = (uint16_t)(L ? L : 1u);
+struct ParseCfg {
+    uint32_t W;            // effective window
+    uint32_t J;            // largest jump: W (variant A) or W + 1 (variant B)
+    int variant;           // RSN_LZSS_ASYNC / RSN_LZSS_ITER
+    const uint32_t *sbits; // variant B: bit p = "a match may start at p" (FindReverse, lzss.go:423-433)
+};
+
+__device__ __forceinline__ bool sbit(const ParseCfg &cfg, size_t g) {
+    return (__ldg(cfg.sbits + (g >> 5)) >> (g & 31)) & 1u;
+}
+
+// jump[p] for the block's positions; positions >= n get 1.
+__device__ __forceinline__ void load_jumps(const ParseCfg &cfg, const uint32_t *__restrict__ lo, size_t start,
+                                           size_t n, uint16_t *jump) {
+    const uint32_t p0 = threadIdx.x * kPI;
+    uint32_t L[kPI];
+    if (start + p0 + kPI <= n) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(lo + start + p0);
+#pragma unroll
+        for (int q = 0; q < kPI / 4; q++) {
+            const uint4 v = __ldg(src + q);
+            L[4 * q] = v.x >> 16;
+            L[4 * q + 1] = v.y >> 16;
+            L[4 * q + 2] = v.z >> 16;
+            L[4 * q + 3] = v.w >> 16;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kPI; k++) L[k] = start + p0 + k < n ? (__ldg(lo + start + p0 + k) >> 16) : 0u;
+    }
+    uint32_t sb = 0;
+    if (cfg.variant == RSN_LZSS_ITER) {  // 16 consecutive S bits (start + p0 is a multiple of 16)
+        sb = (__ldg(cfg.sbits + ((start + p0) >> 5)) >> ((start + p0) & 31)) & 0xFFFFu;
+    }
+#pragma unroll
+    for (int k = 0; k < kPI; k++) {
+        uint32_t j = L[k] ? L[k] : 1u;
+        if (cfg.variant == RSN_LZSS_ITER) j = ((sb >> k) & 1u) ? j + 1 : 1u;
+        jump[p0 + k] = (uint16_t)j;
     }
 }
 
-// x[p] = first chain position (block-relative) at or beyond the end of p's sub-block, or beyond n.
-__device__ __forceinline__ void sub_exits(const uint16_t *jump, uint16_t *x, uint32_t nrel) {
-    const int s = threadIdx.x;  // one thread per sub-block
-    const uint32_t lo_p = s * kPS, hi_p = lo_p + kPS;
-    for (int p = (int)hi_p - 1; p >= (int)lo_p; p--) {
-        uint32_t t = (uint32_t)p + jump[p];
-        x[p] = (uint16_t)((t >= hi_p || t >= nrel) ? t : x[t]);
-    }
-}
-
-// E0[g] = (first chain position at or beyond the block end) - block end, for the chain from g.
-__global__ void __launch_bounds__(kPT) k_parse_exits(const uint32_t *__restrict__ lo, size_t n,
+__global__ void __launch_bounds__(kPT) k_parse_exits(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
                                                      uint16_t *__restrict__ E0) {
-    __shared__ uint16_t jump[kPB];
-    __shared__ uint16_t x[kPB];
+    __shared__ uint16_t y[kPB];
     const size_t start = (size_t)blockIdx.x * kPB;
     const uint32_t nrel = (uint32_t)min((size_t)kPB, n - start);
-    load_jumps(lo, start, n, jump);
+    load_jumps(cfg, lo, start, n, y);
     __syncthreads();
-    sub_exits(jump, x, nrel);
+    const uint32_t p0 = threadIdx.x * kPI;
+#pragma unroll
+    for (int k = 0; k < kPI; k++) y[p0 + k] = (uint16_t)(p0 + k + y[p0 + k]);  // own elements only
     __syncthreads();
-    // compose sub-block exits right to left: later sub-blocks are already final
-    for (int s = kPT - 1; s >= 0; s--) {
-        const int p = s * kPS + threadIdx.x;
-        uint32_t v = x[p];
-        if (v < (uint32_t)kPB && v < nrel) v = x[v];  // v lies in a later, already final sub-block
-        x[p] = (uint16_t)v;
-        __syncthreads();
+    // in-place pointer doubling: y[p] always names a later orbit point of p; racing reads see either
+    // the old or the new value of another element, both valid
+    for (;;) {
+        bool changed = false;
+#pragma unroll
+        for (int k = 0; k < kPI; k++) {
+            const uint32_t v = y[p0 + k];
+            if (v < nrel) {
+                y[p0 + k] = y[v];
+                changed = true;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
     }
-    for (int p = threadIdx.x; p < (int)nrel; p += blockDim.x) {
-        uint32_t v = x[p];
-        E0[start + p] = (uint16_t)(v >= (uint32_t)kPB ? v - kPB : 0u);
+    uint32_t out[kPI];
+#pragma unroll
+    for (int k = 0; k < kPI; k++) {
+        const uint32_t v = y[p0 + k];
+        out[k] = v >= (uint32_t)kPB ? v - kPB : 0u;  // 0: the orbit left the input inside this block
+    }
+    if (p0 + kPI <= nrel) {
+        uint4 *dst = reinterpret_cast<uint4 *>(E0 + start + p0);
+        dst[0] = make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16),
+                            out[6] | (out[7] << 16));
+        dst[1] = make_uint4(out[8] | (out[9] << 16), out[10] | (out[11] << 16), out[12] | (out[13] << 16),
+                            out[14] | (out[15] << 16));
+    } else {
+        for (int k = 0; k < kPI; k++)
+            if (p0 + k < nrel) E0[start + p0 + k] = (uint16_t)out[k];
     }
 }
 
@@ -145,43 +215,43 @@ struct ParseLevels {
     size_t rsize[8];         // region size per level
 };
 
-// one chain step at level `lvl` from absolute position p (p < n, p inside region p / rsize)
+// one orbit step at level `lvl` from absolute position p (p < n, p inside region p / rsize)
 __device__ __forceinline__ size_t level_step(size_t p, int lvl, size_t rsize, const uint16_t *__restrict__ E0,
-                                             const uint16_t *__restrict__ T, uint32_t W) {
+                                             const uint16_t *__restrict__ T, uint32_t J) {
     const size_t r = p / rsize;
     const size_t end = (r + 1) * rsize;
     if (lvl == 0) return end + __ldg(E0 + p);
-    return end + __ldg(T + r * W + (p - r * rsize));
+    return end + __ldg(T + r * (size_t)(J + 1) + (p - r * rsize));
 }
 
-// T_l[r][rel] for rel in [0, W): follow level l-1 until leaving region r (or the input).
+// T_l[r][rel] for rel in [0, J]: follow level l-1 until leaving region r (or the input).
 __global__ void k_parse_up(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tprev,
-                           uint16_t *__restrict__ Tcur, int lvl, size_t rsize_prev, size_t rsize_cur, uint32_t W,
+                           uint16_t *__restrict__ Tcur, int lvl, size_t rsize_prev, size_t rsize_cur, uint32_t J,
                            size_t n) {
     const size_t r = blockIdx.y;
     const uint32_t rel = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rel >= W) return;
+    if (rel > J) return;
     const size_t start = r * rsize_cur, end = start + rsize_cur;
     size_t p = start + rel;
-    while (p < end && p < n) p = level_step(p, lvl - 1, rsize_prev, E0, Tprev, W);
-    Tcur[r * W + rel] = (uint16_t)(p >= end ? p - end : 0);
+    while (p < end && p < n) p = level_step(p, lvl - 1, rsize_prev, E0, Tprev, J);
+    Tcur[r * (size_t)(J + 1) + rel] = (uint16_t)(p >= end ? p - end : 0);
 }
 
 // sequential walk over the (<= kFan) top-level regions
 __global__ void k_parse_top(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Ttop, int lvl,
-                            size_t rsize, size_t regions, uint32_t W, size_t n, uint64_t *__restrict__ entry) {
+                            size_t rsize, size_t regions, uint32_t J, size_t n, uint64_t *__restrict__ entry) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     size_t p = 0;
     for (size_t r = 0; r < regions; r++) {
         entry[r] = p;
         const size_t end = (r + 1) * rsize;
-        if (p < end && p < n) p = level_step(p, lvl, rsize, E0, Ttop, W);
+        if (p < end && p < n) p = level_step(p, lvl, rsize, E0, Ttop, J);
     }
 }
 
 // entries of the children (level lvl-1) of each level-lvl region
 __global__ void k_parse_down(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tchild, int child_lvl,
-                             size_t rsize_child, size_t regions_parent, size_t regions_child, uint32_t W, size_t n,
+                             size_t rsize_child, size_t regions_parent, size_t regions_child, uint32_t J, size_t n,
                              const uint64_t *__restrict__ entry_parent, uint64_t *__restrict__ entry_child) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= regions_parent) return;
@@ -191,17 +261,66 @@ __global__ void k_parse_down(const uint16_t *__restrict__ E0, const uint16_t *__
         if (cr >= regions_child) break;
         entry_child[cr] = p;
         const size_t end = (cr + 1) * rsize_child;
-        if (p < end && p < n) p = level_step(p, child_lvl, rsize_child, E0, Tchild, W);
+        if (p < end && p < n) p = level_step(p, child_lvl, rsize_child, E0, Tchild, J);
     }
 }
 
 // ============================================================================= K4 emit
 
-__device__ __forceinline__ uint32_t token_size(uint32_t packed) {
+__device__ __forceinline__ int ndig_u64(uint64_t v) {
+    int d = 1;
+    while (v >= 10) {
+        v /= 10;
+        d++;
+    }
+    return d;
+}
+
+// What the orbit point g emits.  Variant A (lzss.go:141-150): literal, or token iff strictly
+// shorter than the match, else the raw match.  Variant B (lzss.go:268-289): the match (token iff
+// not longer than the match) followed by the literal that ended it; a literal alone where no match
+// may start.
+struct Tok {
+    uint32_t bytes;   // total bytes emitted at this orbit point
+    uint32_t L;       // match length (0: single literal)
+    uint64_t ptr;     // pointer written in the token
+    bool as_token;    // "<ptr,L>" instead of the raw bytes
+    bool tail;        // variant B: one literal byte follows the match
+};
+
+__device__ __forceinline__ Tok token_at(const ParseCfg &cfg, uint32_t packed, size_t g, size_t n, bool s_ok) {
+    Tok t;
     const uint32_t L = packed >> 16, off = packed & 0xFFFFu;
-    if (L == 0) return 1;
-    const uint32_t tl = 3 + ndig_u32(off) + ndig_u32(L);
-    return tl < L ? tl : L;  // strict '<' (lzss.go:143)
+    t.tail = false;
+    if (cfg.variant == RSN_LZSS_ASYNC) {
+        t.L = L;
+        t.ptr = off;
+        if (L == 0) {
+            t.as_token = false;
+            t.bytes = 1;
+            return t;
+        }
+        const uint32_t tl = 3 + ndig_u32(off) + ndig_u32(L);
+        t.as_token = tl < L;  // strict '<' (lzss.go:143)
+        t.bytes = t.as_token ? tl : L;
+        return t;
+    }
+    if (!s_ok) {  // FindReverse found nothing: plain literal (lzss.go:289)
+        t.L = 0;
+        t.ptr = 0;
+        t.as_token = false;
+        t.bytes = 1;
+        return t;
+    }
+    const uint32_t Lb = L ? L : 1u;
+    t.L = Lb;
+    // lzss.go:256: pointer = len(searchBuffer) - (index inside the WINDOW slice)
+    t.ptr = Lb >= 2 ? (uint64_t)off + (g > cfg.W ? g - cfg.W : 0) : 1;
+    const uint32_t tl = 3 + ndig_u64(t.ptr) + ndig_u32(Lb);
+    t.as_token = Lb >= 2 && tl <= Lb;  // '<=' (lzss.go:272); a 1-byte match is never shorter as a token
+    t.tail = g + Lb < n;
+    t.bytes = (t.as_token ? tl : Lb) + (t.tail ? 1u : 0u);
+    return t;
 }
 
 __device__ __forceinline__ uint8_t *put_dec(uint8_t *o, uint32_t v) {
@@ -213,68 +332,171 @@ __device__ __forceinline__ uint8_t *put_dec(uint8_t *o, uint32_t v) {
     return o + d;
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(kPT) k_emit(const uint8_t *__restrict__ enc, const uint32_t *__restrict__ lo,
-                                              size_t n, const uint64_t *__restrict__ entry0,
-                                              uint64_t *__restrict__ blk_bytes, const uint64_t *__restrict__ blk_off,
-                                              uint8_t *__restrict__ out) {
-    __shared__ uint16_t jump[kPB];
-    __shared__ uint16_t x[kPB];
-    __shared__ uint32_t sub_entry[kPT];
+__device__ __forceinline__ uint8_t *put_dec64(uint8_t *o, uint64_t v) {
+    const int d = ndig_u64(v);
+    for (int k = d - 1; k >= 0; k--) {
+        o[k] = (uint8_t)('0' + v % 10);
+        v /= 10;
+    }
+    return o + d;
+}
+
+// visited bitmap (one u16 per 16 positions) and output bytes of every block
+__global__ void __launch_bounds__(kPT) k_emit_plan(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
+                                                   const uint64_t *__restrict__ entry0,
+                                                   uint16_t *__restrict__ visited, uint64_t *__restrict__ blk_bytes) {
+    __shared__ uint16_t ya[kPB], yb[kPB];
+    __shared__ uint8_t mark[kPB];
     __shared__ uint32_t sm[33];
     const size_t start = (size_t)blockIdx.x * kPB;
     const uint32_t nrel = (uint32_t)min((size_t)kPB, n - start);
-    load_jumps(lo, start, n, jump);
+    const uint32_t p0 = threadIdx.x * kPI;
+    load_jumps(cfg, lo, start, n, ya);
     __syncthreads();
-    sub_exits(jump, x, nrel);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint64_t e0 = entry0[blockIdx.x];
-        uint32_t e = (e0 - start) > 0xFFFFull ? 0xFFFFu : (uint32_t)(e0 - start);  // may lie beyond this block
-        for (int s = 0; s < kPT; s++) {
-            sub_entry[s] = e;
-            if (e < (uint32_t)(s + 1) * kPS && e < nrel) e = x[e];
-        }
+#pragma unroll
+    for (int k = 0; k < kPI; k++) {
+        ya[p0 + k] = (uint16_t)(p0 + k + ya[p0 + k]);
+        mark[p0 + k] = 0;
     }
     __syncthreads();
-    const uint32_t hi = (threadIdx.x + 1) * kPS;
-    uint32_t bytes = 0;
-    for (uint32_t p = sub_entry[threadIdx.x]; p < hi && p < nrel; p += jump[p]) bytes += token_size(__ldg(lo + start + p));
+    {
+        const uint64_t e = entry0[blockIdx.x];
+        if (threadIdx.x == 0 && e >= start && e - start < nrel) mark[e - start] = 1;
+    }
+    __syncthreads();
+    uint16_t *y = ya, *yn = yb;
+    for (;;) {
+        // scatter: y = jump^(2^r); every marked point marks its 2^r-th successor
+#pragma unroll
+        for (int k = 0; k < kPI; k++) {
+            const uint32_t v = y[p0 + k];
+            if (mark[p0 + k] && v < nrel) mark[v] = 1;
+        }
+        bool live = false;
+#pragma unroll
+        for (int k = 0; k < kPI; k++) {
+            const uint32_t v = y[p0 + k];
+            const uint32_t v2 = v < nrel ? y[v] : v;
+            yn[p0 + k] = (uint16_t)v2;
+            live |= v < nrel;
+        }
+        if (!__syncthreads_or(live)) break;
+        uint16_t *t = y;
+        y = yn;
+        yn = t;
+    }
+    // sizes of the orbit points I own
+    uint32_t bits = 0, bytes = 0;
+#pragma unroll
+    for (int k = 0; k < kPI; k++) {
+        if (p0 + k < nrel && mark[p0 + k]) {
+            const size_t g = start + p0 + k;
+            bits |= 1u << k;
+            const bool s_ok = cfg.variant == RSN_LZSS_ITER ? sbit(cfg, g) : true;
+            bytes += token_at(cfg, __ldg(lo + g), g, n, s_ok).bytes;
+        }
+    }
+    visited[(start >> 4) + threadIdx.x] = (uint16_t)bits;
     uint32_t total;
-    uint32_t pre = block_exclusive_sum<uint32_t>(bytes, sm, total);
-    if (!WRITE) {
-        if (threadIdx.x == 0) blk_bytes[blockIdx.x] = total;
-        return;
+    block_exclusive_sum<uint32_t>(bytes, sm, total);
+    if (threadIdx.x == 0) blk_bytes[blockIdx.x] = total;
+}
+
+constexpr int kStage = kPB + 64;  // output bytes of one block never exceed consumed + one token
+
+__global__ void __launch_bounds__(kPT) k_emit_write(ParseCfg cfg, const uint8_t *__restrict__ enc,
+                                                    const uint32_t *__restrict__ lo, size_t n,
+                                                    const uint16_t *__restrict__ visited,
+                                                    const uint64_t *__restrict__ blk_off, uint8_t *__restrict__ out) {
+    __shared__ __align__(16) uint8_t stage[kStage];
+    __shared__ uint32_t sm[33];
+    const size_t start = (size_t)blockIdx.x * kPB;
+    const uint32_t p0 = threadIdx.x * kPI;
+    const uint32_t bits = visited[(start >> 4) + threadIdx.x];
+    uint32_t bytes = 0;
+    for (uint32_t b = bits; b; b &= b - 1) {
+        const int k = __ffs(b) - 1;
+        const size_t g = start + p0 + k;
+        const bool s_ok = cfg.variant == RSN_LZSS_ITER ? sbit(cfg, g) : true;
+        bytes += token_at(cfg, __ldg(lo + g), g, n, s_ok).bytes;
     }
-    uint8_t *o = out + blk_off[blockIdx.x] + pre;
-    for (uint32_t p = sub_entry[threadIdx.x]; p < hi && p < nrel; p += jump[p]) {
-        const size_t g = start + p;
-        const uint32_t packed = __ldg(lo + g);
-        const uint32_t L = packed >> 16, off = packed & 0xFFFFu;
-        if (L == 0) {
-            *o++ = enc[g];
+    uint32_t total;
+    uint32_t pos = block_exclusive_sum<uint32_t>(bytes, sm, total);
+    for (uint32_t b = bits; b; b &= b - 1) {
+        const int k = __ffs(b) - 1;
+        const size_t g = start + p0 + k;
+        const bool s_ok = cfg.variant == RSN_LZSS_ITER ? sbit(cfg, g) : true;
+        const Tok t = token_at(cfg, __ldg(lo + g), g, n, s_ok);
+        uint8_t *o = stage + pos;
+        if (t.L == 0) {
+            *o++ = __ldg(enc + g);
+        } else if (t.as_token) {
+            *o++ = '<';
+            o = put_dec64(o, t.ptr);
+            *o++ = ',';
+            o = put_dec(o, t.L);
+            *o++ = '>';
         } else {
-            const uint32_t tl = 3 + ndig_u32(off) + ndig_u32(L);
-            if (tl < L) {
-                *o++ = '<';
-                o = put_dec(o, off);
-                *o++ = ',';
-                o = put_dec(o, L);
-                *o++ = '>';
-            } else {
-                for (uint32_t k = 0; k < L; k++) o[k] = enc[g + k];
-                o += L;
-            }
+            for (uint32_t q = 0; q < t.L; q++) o[q] = __ldg(enc + g + q);
+            o += t.L;
         }
+        if (t.tail) *o++ = __ldg(enc + g + t.L);
+        pos += t.bytes;
     }
+    __syncthreads();
+    uint8_t *dst = out + blk_off[blockIdx.x];
+    // coalesced copy: byte head up to 16-byte alignment of dst, then 16-byte vectors, then tail
+    const uint32_t mis = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+    const uint32_t head = min(mis, total);
+    for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = stage[i];
+    const uint32_t nvec = (total - head) / 16;
+    for (uint32_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+        const uint8_t *sp = stage + head + v * 16;  // shared side may be unaligned: assemble words
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            w[q] = (uint32_t)sp[4 * q] | ((uint32_t)sp[4 * q + 1] << 8) | ((uint32_t)sp[4 * q + 2] << 16) |
+                   ((uint32_t)sp[4 * q + 3] << 24);
+        *reinterpret_cast<uint4 *>(dst + head + v * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (uint32_t i = head + nvec * 16 + threadIdx.x; i < total; i += blockDim.x) dst[i] = stage[i];
+}
+
+// ============================================================================= variant B: start bits
+
+// firstpos[b][parity] = first position of byte b at that position parity (FindReverse scans the
+// WHOLE history with stride 2, lzss.go:423-433, so a match may start at p iff byte enc[p] occurs
+// earlier at a position of parity (p-1) mod 2).
+__global__ void __launch_bounds__(256) k_first_pos(const uint8_t *__restrict__ enc, size_t n,
+                                                   unsigned long long *__restrict__ firstpos) {
+    __shared__ unsigned long long best[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) best[i] = ~0ull;
+    __syncthreads();
+    const size_t chunk = 8192;
+    const size_t lo_p = (size_t)blockIdx.x * chunk, hi_p = min(n, lo_p + chunk);
+    for (size_t p = lo_p + threadIdx.x; p < hi_p; p += blockDim.x)
+        atomicMin(&best[(uint32_t)enc[p] * 2 + (p & 1)], (unsigned long long)p);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 512; i += blockDim.x)
+        if (best[i] != ~0ull) atomicMin(&firstpos[i], best[i]);
+}
+
+__global__ void __launch_bounds__(256) k_start_bits(const uint8_t *__restrict__ enc, size_t n,
+                                                    const unsigned long long *__restrict__ firstpos,
+                                                    uint32_t *__restrict__ sbits) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (p < n && p > 0) ok = firstpos[(uint32_t)enc[p] * 2 + ((p - 1) & 1)] < p;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && p < n + 32) sbits[p >> 5] = m;
 }
 
 // ============================================================================= host orchestration
 
-static int parse_and_emit(const uint8_t *d_enc, size_t n, uint32_t W, const uint32_t *d_lo, uint8_t **d_out,
+static int parse_and_emit(const uint8_t *d_enc, size_t n, ParseCfg cfg, const uint32_t *d_lo, uint8_t **d_out,
                           size_t *out_n, cudaStream_t s) {
     const size_t blocks = div_up(n, kPB);
-    // level geometry
+    const uint32_t J = cfg.J;
     ParseLevels lv;
     lv.top = 0;
     lv.rsize[0] = kPB;
@@ -285,34 +507,36 @@ static int parse_and_emit(const uint8_t *d_enc, size_t n, uint32_t W, const uint
         lv.top++;
     }
     DevBuf E0, T[8], entry[8];
-    RSN_TRY(E0.alloc(n * 2 + 16, s));
-    RSN_LAUNCH(k_parse_exits, (unsigned)blocks, kPT, 0, s, d_lo, n, E0.as<uint16_t>());
+    RSN_TRY(E0.alloc(blocks * kPB * 2 + 64, s));
+    RSN_LAUNCH(k_parse_exits, (unsigned)blocks, kPT, 0, s, cfg, d_lo, n, E0.as<uint16_t>());
     for (int l = 1; l <= lv.top; l++) {
-        RSN_TRY(T[l].alloc(lv.regions[l] * W * 2, s));
-        dim3 grid((unsigned)div_up(W, 256), (unsigned)lv.regions[l]);
+        RSN_TRY(T[l].alloc(lv.regions[l] * (size_t)(J + 1) * 2, s));
+        dim3 grid((unsigned)div_up((size_t)J + 1, 256), (unsigned)lv.regions[l]);
         RSN_LAUNCH(k_parse_up, grid, 256, 0, s, E0.as<uint16_t>(), T[l - 1].as<uint16_t>(), T[l].as<uint16_t>(), l,
-                   lv.rsize[l - 1], lv.rsize[l], W, n);
+                   lv.rsize[l - 1], lv.rsize[l], J, n);
     }
     for (int l = 0; l <= lv.top; l++) RSN_TRY(entry[l].alloc(lv.regions[l] * 8, s));
     RSN_LAUNCH(k_parse_top, 1, 32, 0, s, E0.as<uint16_t>(), T[lv.top].as<uint16_t>(), lv.top, lv.rsize[lv.top],
-               lv.regions[lv.top], W, n, entry[lv.top].as<uint64_t>());
+               lv.regions[lv.top], J, n, entry[lv.top].as<uint64_t>());
     for (int l = lv.top; l >= 1; l--) {
         RSN_LAUNCH(k_parse_down, (unsigned)div_up(lv.regions[l], 128), 128, 0, s, E0.as<uint16_t>(),
-                   T[l - 1].as<uint16_t>(), l - 1, lv.rsize[l - 1], lv.regions[l], lv.regions[l - 1], W, n,
+                   T[l - 1].as<uint16_t>(), l - 1, lv.rsize[l - 1], lv.regions[l], lv.regions[l - 1], J, n,
                    entry[l].as<uint64_t>(), entry[l - 1].as<uint64_t>());
     }
-    DevBuf bb, bo;
+    DevBuf vis, bb, bo;
+    RSN_TRY(vis.alloc(blocks * (kPB / 16) * 2 + 16, s));
     RSN_TRY(bb.alloc(blocks * 8, s));
     RSN_TRY(bo.alloc((blocks + 1) * 8, s));
-    RSN_LAUNCH(k_emit<false>, (unsigned)blocks, kPT, 0, s, d_enc, d_lo, n, entry[0].as<uint64_t>(), bb.as<uint64_t>(),
-               (const uint64_t *)nullptr, (uint8_t *)nullptr);
+    RSN_LAUNCH(k_emit_plan, (unsigned)blocks, kPT, 0, s, cfg, d_lo, n, entry[0].as<uint64_t>(), vis.as<uint16_t>(),
+               bb.as<uint64_t>());
+    E0.reset();
     RSN_TRY(spine_scan_u64(bb.as<uint64_t>(), bo.as<uint64_t>(), bo.as<uint64_t>() + blocks, blocks, s));
     uint64_t total = 0;
     RSN_TRY(read_u64(bo.as<uint64_t>() + blocks, &total, s));
     DevBuf out;
     RSN_TRY(out.alloc(total + 16, s));
-    RSN_LAUNCH(k_emit<true>, (unsigned)blocks, kPT, 0, s, d_enc, d_lo, n, entry[0].as<uint64_t>(),
-               (uint64_t *)nullptr, bo.as<uint64_t>(), out.as<uint8_t>());
+    RSN_LAUNCH(k_emit_write, (unsigned)blocks, kPT, 0, s, cfg, d_enc, d_lo, n, vis.as<uint16_t>(), bo.as<uint64_t>(),
+               out.as<uint8_t>());
     *d_out = (uint8_t *)out.release();
     *out_n = (size_t)total;
     return RSN_OK;
@@ -330,10 +554,11 @@ int lzss_effective_window(int64_t window, size_t enc_n, uint32_t *W) {
 
 int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant, uint8_t **d_out, size_t *out_n,
                       cudaStream_t s) {
-    if (variant != RSN_LZSS_ASYNC) return RSN_ERR_UNSUPPORTED;  // variant B: planned
-    DevBuf enc;
+    if (variant != RSN_LZSS_ASYNC && variant != RSN_LZSS_ITER) return RSN_ERR_INVALID_ARG;
+    DevBuf enc_buf;
+    const uint8_t *enc = nullptr;
     size_t en = 0;
-    RSN_TRY(lzss_escape(d_in, n, enc, &en, s));
+    RSN_TRY(lzss_escape(d_in, n, enc_buf, &enc, &en, s));
     if (en == 0) {
         DevBuf out;
         RSN_TRY(out.alloc(16, s));
@@ -343,10 +568,23 @@ int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant
     }
     uint32_t W = 0;
     RSN_TRY(lzss_effective_window(window, en, &W));
-    DevBuf lo;
-    RSN_TRY(lo.alloc(en * 4 + 16, s));
-    RSN_TRY(lzss_match(enc.as<uint8_t>(), en, W, lo.as<uint32_t>(), s));
-    return parse_and_emit(enc.as<uint8_t>(), en, W, lo.as<uint32_t>(), d_out, out_n, s);
+    DevBuf lo, sbits, fp;
+    RSN_TRY(lo.alloc(div_up(en, kPB) * kPB * 4 + 64, s));
+    RSN_TRY(lzss_match(enc, en, W, lo.as<uint32_t>(), s));
+    ParseCfg cfg{W, W, variant, nullptr};
+    if (variant == RSN_LZSS_ITER) {
+        cfg.J = W + 1;
+        RSN_TRY(fp.alloc(512 * 8, s));
+        const size_t sb_bytes = (div_up(en, kPB) * kPB / 32 + 4) * 4;  // whole blocks: load_jumps reads 16-bit groups
+        RSN_TRY(sbits.alloc(sb_bytes, s));
+        RSN_CUDA(cudaMemsetAsync(sbits.p, 0, sb_bytes, s));
+        RSN_CUDA(cudaMemsetAsync(fp.p, 0xFF, 512 * 8, s));
+        RSN_LAUNCH(k_first_pos, (unsigned)div_up(en, 8192), 256, 0, s, enc, en, fp.as<unsigned long long>());
+        RSN_LAUNCH(k_start_bits, (unsigned)div_up(en + 31, 256), 256, 0, s, enc, en, fp.as<unsigned long long>(),
+                   sbits.as<uint32_t>());
+        cfg.sbits = sbits.as<uint32_t>();
+    }
+    return parse_and_emit(enc, en, cfg, lo.as<uint32_t>(), d_out, out_n, s);
 }
 
 }  // namespace rsn

@@ -37,12 +37,39 @@ def test_compress_async_cases(rsn, oracle, name):
     assert rsn.lz.Decompress(got1k, False) == data
 
 
+@pytest.mark.parametrize("name", sorted(GOLDEN["lzss"]))
+def test_compress_iter_cases(rsn, oracle, name):
+    """The exported lz.Compress (variant B, lzss.go:224-316) with all its quirks: stride-2 start
+    search over the whole history, the literal after every match, `<=` emit rule, and the pointer
+    computed from the window-relative index (lossy once the input is longer than the window)."""
+    data = cases.lzss_cases()[name]
+    got = rsn.lz.Compress(data, False, 4096)
+    assert got == oracle.lzss_compress_iter(data, 4096)
+    matches(GOLDEN["lzss"][name]["iter_w4096"], got)
+    for w in (1024, 8192):
+        assert rsn.lz.Compress(data, False, w) == oracle.lzss_compress_iter(data, w)
+
+
+def test_compress_iter_reference_test_shape(rsn, oracle):
+    """lzss_test.go:25-35: Decompress(Compress(x, false, 8192)) == x for a text shorter than the window."""
+    data = cases.lzss_cases()["text_8k"][:3461]
+    comp = rsn.lz.Compress(data, False, 8192)
+    assert comp == oracle.lzss_compress_iter(data, 8192)
+    assert rsn.lz.Decompress(comp, False) == data
+
+
+def test_compress_iter_large(rsn, oracle):
+    data = synth.mixed(1 << 20, 41, segment=1 << 18)
+    assert rsn.lz.Compress(data, False, 4096) == oracle.lzss_compress_iter(data, 4096)
+
+
 @pytest.mark.parametrize("window", [1, 2, 3, 7, 64, 100, 4095, 4097, 8192, 0, -1])
 def test_windows(rsn, oracle, window):
     data = cases.lzss_cases()["text_8k"] + cases.lzss_cases()["period3"] + b"<\\" * 20
     got = rsn.lz.CompressAsync(data, False, window)
     assert got == oracle.lzss_compress_async(data, window)
     assert rsn.lz.Decompress(got) == data
+    assert rsn.lz.Compress(data, False, window) == oracle.lzss_compress_iter(data, window)
 
 
 def test_match_arrays(rsn, oracle):
