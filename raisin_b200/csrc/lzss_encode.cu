@@ -158,24 +158,33 @@ __device__ __forceinline__ void load_jumps(const ParseCfg &cfg, const uint32_t *
     if (cfg.variant == RSN_LZSS_ITER) {  // 16 consecutive S bits (start + p0 is a multiple of 16)
         sb = (__ldg(cfg.sbits + ((start + p0) >> 5)) >> ((start + p0) & 31)) & 0xFFFFu;
     }
+    uint32_t w[kPI / 2];
 #pragma unroll
     for (int k = 0; k < kPI; k++) {
         uint32_t j = L[k] ? L[k] : 1u;
         if (cfg.variant == RSN_LZSS_ITER) j = ((sb >> k) & 1u) ? j + 1 : 1u;
-        jump[p0 + k] = (uint16_t)j;
+        if (k & 1) w[k >> 1] |= j << 16;
+        else w[k >> 1] = j;
     }
+    uint4 *dst = reinterpret_cast<uint4 *>(jump + p0);  // jump[] is 16-byte aligned, p0 a multiple of 16
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 __global__ void __launch_bounds__(kPT) k_parse_exits(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
                                                      uint16_t *__restrict__ E0) {
-    __shared__ uint16_t y[kPB];
+    __shared__ __align__(16) uint16_t y[kPB];
     const size_t start = (size_t)blockIdx.x * kPB;
     const uint32_t nrel = (uint32_t)min((size_t)kPB, n - start);
     load_jumps(cfg, lo, start, n, y);
     __syncthreads();
     const uint32_t p0 = threadIdx.x * kPI;
+    // from here on a thread owns the interleaved elements k*kPT + tid (conflict-free shared access)
 #pragma unroll
-    for (int k = 0; k < kPI; k++) y[p0 + k] = (uint16_t)(p0 + k + y[p0 + k]);  // own elements only
+    for (int k = 0; k < kPI; k++) {
+        const uint32_t p = k * kPT + threadIdx.x;
+        y[p] = (uint16_t)(p + y[p]);
+    }
     __syncthreads();
     // in-place pointer doubling: y[p] always names a later orbit point of p; racing reads see either
     // the old or the new value of another element, both valid
@@ -183,19 +192,24 @@ __global__ void __launch_bounds__(kPT) k_parse_exits(ParseCfg cfg, const uint32_
         bool changed = false;
 #pragma unroll
         for (int k = 0; k < kPI; k++) {
-            const uint32_t v = y[p0 + k];
+            const uint32_t p = k * kPT + threadIdx.x;
+            const uint32_t v = y[p];
             if (v < nrel) {
-                y[p0 + k] = y[v];
+                y[p] = y[v];
                 changed = true;
             }
         }
         if (!__syncthreads_or(changed)) break;
     }
     uint32_t out[kPI];
+    {
+        const uint4 a = reinterpret_cast<const uint4 *>(y + p0)[0], b = reinterpret_cast<const uint4 *>(y + p0)[1];
+        const uint32_t yw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int k = 0; k < kPI; k++) {
-        const uint32_t v = y[p0 + k];
-        out[k] = v >= (uint32_t)kPB ? v - kPB : 0u;  // 0: the orbit left the input inside this block
+        for (int k = 0; k < kPI; k++) {
+            const uint32_t v = (yw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+            out[k] = v >= (uint32_t)kPB ? v - kPB : 0u;  // 0: the orbit left the input inside this block
+        }
     }
     if (p0 + kPI <= nrel) {
         uint4 *dst = reinterpret_cast<uint4 *>(E0 + start + p0);
@@ -345,8 +359,8 @@ __device__ __forceinline__ uint8_t *put_dec64(uint8_t *o, uint64_t v) {
 __global__ void __launch_bounds__(kPT) k_emit_plan(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
                                                    const uint64_t *__restrict__ entry0,
                                                    uint16_t *__restrict__ visited, uint64_t *__restrict__ blk_bytes) {
-    __shared__ uint16_t ya[kPB], yb[kPB];
-    __shared__ uint8_t mark[kPB];
+    __shared__ __align__(16) uint16_t ya[kPB], yb[kPB];
+    __shared__ __align__(16) uint8_t mark[kPB];
     __shared__ uint32_t sm[33];
     const size_t start = (size_t)blockIdx.x * kPB;
     const uint32_t nrel = (uint32_t)min((size_t)kPB, n - start);
@@ -354,9 +368,10 @@ __global__ void __launch_bounds__(kPT) k_emit_plan(ParseCfg cfg, const uint32_t 
     load_jumps(cfg, lo, start, n, ya);
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kPI; k++) {
-        ya[p0 + k] = (uint16_t)(p0 + k + ya[p0 + k]);
-        mark[p0 + k] = 0;
+    for (int k = 0; k < kPI; k++) {  // interleaved ownership: conflict-free shared access
+        const uint32_t p = k * kPT + threadIdx.x;
+        ya[p] = (uint16_t)(p + ya[p]);
+        mark[p] = 0;
     }
     __syncthreads();
     {
@@ -367,29 +382,31 @@ __global__ void __launch_bounds__(kPT) k_emit_plan(ParseCfg cfg, const uint32_t 
     uint16_t *y = ya, *yn = yb;
     for (;;) {
         // scatter: y = jump^(2^r); every marked point marks its 2^r-th successor
-#pragma unroll
-        for (int k = 0; k < kPI; k++) {
-            const uint32_t v = y[p0 + k];
-            if (mark[p0 + k] && v < nrel) mark[v] = 1;
-        }
         bool live = false;
 #pragma unroll
         for (int k = 0; k < kPI; k++) {
-            const uint32_t v = y[p0 + k];
-            const uint32_t v2 = v < nrel ? y[v] : v;
-            yn[p0 + k] = (uint16_t)v2;
-            live |= v < nrel;
+            const uint32_t p = k * kPT + threadIdx.x;
+            const uint32_t v = y[p];
+            if (v < nrel) {
+                if (mark[p]) mark[v] = 1;
+                yn[p] = y[v];
+                live = true;
+            } else {
+                yn[p] = (uint16_t)v;
+            }
         }
         if (!__syncthreads_or(live)) break;
         uint16_t *t = y;
         y = yn;
         yn = t;
     }
-    // sizes of the orbit points I own
+    // sizes of the orbit points of my 16 consecutive positions
     uint32_t bits = 0, bytes = 0;
+    const uint4 mk = *reinterpret_cast<const uint4 *>(mark + p0);
+    const uint32_t mkw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
     for (int k = 0; k < kPI; k++) {
-        if (p0 + k < nrel && mark[p0 + k]) {
+        if (p0 + k < nrel && ((mkw[k >> 2] >> ((k & 3) * 8)) & 0xFFu)) {
             const size_t g = start + p0 + k;
             bits |= 1u << k;
             const bool s_ok = cfg.variant == RSN_LZSS_ITER ? sbit(cfg, g) : true;

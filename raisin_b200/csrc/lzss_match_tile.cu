@@ -130,6 +130,28 @@ __device__ __forceinline__ void radix_pass(Smem &sm, const uint8_t *s, const uin
     __syncthreads();
 }
 
+// Candidates of the sorted slot r (entry e): the slots [lo, r) of its 3-gram group whose positions
+// lie inside the window, in position order (farthest first).
+__device__ __forceinline__ void slot_range(const Smem &sm, const uint16_t *arr, uint32_t r, uint32_t e, uint32_t W,
+                                           uint32_t &lo_out, uint32_t &cnt_out) {
+    // start of the group: highest head bit at or below r
+    uint32_t wi = r >> 5;
+    uint32_t bits = sm.heads[wi] & (0xFFFFFFFFu >> (31 - (r & 31)));
+    while (bits == 0) bits = sm.heads[--wi];
+    uint32_t lo = (wi << 5) + (31 - __clz(bits)), hi = r;
+    // first candidate inside the window: lowest slot in [group start, r) with position >= e - W
+    if (e > W && lo < hi && arr[lo] < e - W) {
+        const uint32_t minpos = e - W;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (arr[mid] < minpos) lo = mid + 1;
+            else hi = mid;
+        }
+    }
+    lo_out = lo;
+    cnt_out = r - lo;
+}
+
 }  // namespace tile
 
 __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
@@ -210,74 +232,101 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
     // ---- pass 3: by the 3-gram  ->  candidate lists in position order
     radix_pass(sm, s, sm.a, sm.b, ev, 0);
     const uint16_t *arr = sm.b;  // sorted by (3-gram, position)
-    uint16_t *list = sm.a;       // spare buffer: the sorted slots that belong to the tile, compacted
-    // group heads + per-warp count of tile slots
+    uint16_t *order = sm.a;      // spare buffer: tile slots that have candidates, grouped by work class
+    // ---- group heads
     {
         const uint32_t per = ((ev + WARPS - 1) / WARPS + 31) & ~31u;
         const uint32_t lo = min(ev, w * per), hi = min(ev, lo + per);
-        uint32_t mine = 0;
         for (uint32_t c = lo; c < hi; c += 32) {
             const uint32_t r = c + lane;
-            bool head = false, in_tile = false;
-            if (r < hi) {
-                const uint32_t e = arr[r];
-                head = r == 0 || ((lds32(s, e) ^ lds32(s, arr[r - 1])) & 0xFFFFFFu) != 0;
-                in_tile = e >= halo;
-            }
+            bool head = false;
+            if (r < hi) head = r == 0 || ((lds32(s, arr[r]) ^ lds32(s, arr[r - 1])) & 0xFFFFFFu) != 0;
             const unsigned hm = __ballot_sync(0xffffffffu, head);
-            const unsigned tm = __ballot_sync(0xffffffffu, in_tile);
             if (lane == 0) sm.heads[c >> 5] = hm;
-            mine += __popc(tm);
-        }
-        if (lane == 0) sm.wtot[w] = mine;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t run = 0;
-            for (int k = 0; k < WARPS; k++) {
-                const uint32_t v = sm.wtot[k];
-                sm.wtot[k] = run;
-                run += v;
-            }
-            sm.wtot[WARPS] = run;
-        }
-        __syncthreads();
-        uint32_t out = sm.wtot[w];
-        for (uint32_t c = lo; c < hi; c += 32) {
-            const uint32_t r = c + lane;
-            const bool in_tile = r < hi && arr[r] >= halo;
-            const unsigned tm = __ballot_sync(0xffffffffu, in_tile);
-            if (in_tile) list[out + __popc(tm & ((1u << lane) - 1))] = (uint16_t)r;
-            out += __popc(tm);
         }
     }
+    for (int i = threadIdx.x; i < 16 * WARPS; i += THREADS) sm.cnt[i] = 0;
     __syncthreads();
-    const uint32_t n_list = sm.wtot[WARPS];
+    // ---- per tile slot: candidate range, work class.  Slots without candidates are final here.
+    // Lanes of a warp later take slots of ONE class (similar candidate counts), which is what keeps
+    // the candidate loop from idling most lanes behind the few slots of very frequent 3-grams.
+    {
+        const unsigned lt = (1u << lane) - 1;
+        const uint32_t per = ((ev + WARPS - 1) / WARPS + 31) & ~31u;
+        const uint32_t lo_s = min(ev, w * per), hi_s = min(ev, lo_s + per);
+        for (int phase = 0; phase < 2; phase++) {
+            for (uint32_t c0 = lo_s; c0 < hi_s; c0 += 32) {
+                const uint32_t r = c0 + lane;
+                uint32_t cls = 0xFF;
+                if (phase == 0) {
+                    if (r < hi_s) {
+                        const uint32_t e = arr[r];
+                        if (e >= halo) {
+                            uint32_t lo, cnt;
+                            slot_range(sm, arr, r, e, W, lo, cnt);
+                            if (cnt == 0) {  // no earlier occurrence of this 3-gram in the window
+                                packed[base + e] = (uint32_t)sm.lowL[e - halo] << 16;
+                                sm.lowL[e - halo] = 0xFF;
+                            } else {
+                                cls = 31 - __clz(cnt);  // 0..12: floor(log2(count))
+                                cls = cls > 7 ? 7 : cls;
+                            }
+                        }
+                        sm.info[r] = (uint8_t)cls;
+                    }
+                } else if (r < hi_s) {
+                    cls = sm.info[r];
+                }
+                const bool act = cls != 0xFF;
+                unsigned peers = __ballot_sync(0xffffffffu, act);
+#pragma unroll
+                for (int bit = 0; bit < 3; bit++) {
+                    const unsigned m = __ballot_sync(0xffffffffu, (cls >> bit) & 1u);
+                    peers &= ((cls >> bit) & 1u) ? m : ~m;
+                }
+                if (act) {
+                    const uint32_t rank = __popc(peers & lt);
+                    const bool last = (peers >> lane) == 1u;
+                    if (phase == 0) {
+                        if (last) sm.cnt[cls * WARPS + w] += (uint16_t)(rank + 1);
+                    } else {
+                        const uint32_t basev = sm.cnt[cls * WARPS + w];
+                        order[basev + rank] = (uint16_t)r;
+                        __syncwarp(peers);
+                        if (last) sm.cnt[cls * WARPS + w] = (uint16_t)(basev + rank + 1);
+                    }
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            if (phase == 0) {
+                if (threadIdx.x == 0) {  // exclusive scan of the 8 x WARPS class counters, class-major
+                    uint32_t run = 0;
+                    for (int k = 0; k < 8 * WARPS; k++) {
+                        const uint32_t v = sm.cnt[k];
+                        sm.cnt[k] = (uint16_t)run;
+                        run += v;
+                    }
+                    sm.wtot[0] = run;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    const uint32_t n_order = sm.wtot[0];
 
-    // ---- candidates, far to near; one thread per tile slot, in sorted order (neighbouring lanes
-    // sit in the same 3-gram group, so their candidate counts are similar)
-    for (uint32_t k0 = w * 32; k0 < n_list; k0 += THREADS) {
+    // ---- candidates, far to near; one thread per slot, slots of similar work side by side
+    for (uint32_t k0 = w * 32; k0 < n_order; k0 += THREADS) {
         const uint32_t k = k0 + lane;
-        const bool act = k < n_list;
+        const bool act = k < n_order;
         uint32_t r = 0, e = 0, room = 0, c = 0, best = 3, boff = 0;
         bool has3 = false;
         if (act) {
-            r = list[k];
+            r = order[k];
             e = arr[r];
             room = (uint32_t)min((size_t)W, n - (base + e));
-            // start of my group: highest head bit at or below r
-            uint32_t wi = r >> 5;
-            uint32_t bits = sm.heads[wi] & (0xFFFFFFFFu >> (31 - (r & 31)));
-            while (bits == 0) bits = sm.heads[--wi];
-            uint32_t lo = (wi << 5) + (31 - __clz(bits)), hi = r;
-            // first candidate inside the window: lowest slot in [group start, r) with position >= e - W
-            if (e > W && lo < hi && arr[lo] < e - W) {
-                const uint32_t minpos = e - W;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (arr[mid] < minpos) lo = mid + 1;
-                    else hi = mid;
-                }
-            }
+            uint32_t lo, cnt;
+            slot_range(sm, arr, r, e, W, lo, cnt);
             c = lo;
             // arr[lo] is the farthest candidate: a 3-byte match exists iff its distance is >= 3
             has3 = lo < r && e - arr[lo] >= 3;
