@@ -331,32 +331,17 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
             // arr[lo] is the farthest candidate: a 3-byte match exists iff its distance is >= 3
             has3 = lo < r && e - arr[lo] >= 3;
         }
-        // Each round: every lane skips ahead to its next candidate that can still beat `best`
-        // (cheap, divergent), then all such lanes extend their match together.
-        // Invariants of the skip loop: a candidate at distance d yields at most min(d, room), so
-        // only slots with arr[c] < jlim = e - best can win (the list is in position order), and a
-        // winner must match the byte at offset `best` (tgt).
-        uint32_t jlim = e - best;            // candidates at j >= jlim have d <= best
-        if (room <= best) c = r;             // nothing can be longer than `room`
-        const uint8_t *sb = s + best;
-        uint32_t tgt = act ? s[e + best] : 0;
-        for (;;) {
-            uint32_t j = 0;
-            bool pend = false;
-            while (c < r) {
-                j = arr[c];
-                if (j >= jlim) {  // nearer candidates yield even less
-                    c = r;
-                    break;
-                }
-                if (sb[j] == tgt) {
-                    pend = true;
-                    break;
-                }
-                c++;
-            }
-            if (!__any_sync(0xffffffffu, pend)) break;
-            if (pend) {
+        // Far to near.  A candidate at distance d yields at most min(d, room), so only slots with
+        // arr[c] < jlim = e - best can win (the list is in position order), and a winner must match
+        // the byte at offset `best` (tgt).  Lanes of a warp hold slots of one work class.
+        if (act && room > best) {
+            uint32_t jlim = e - best;
+            const uint8_t *sb = s + best;
+            uint32_t tgt = s[e + best];
+            for (; c < r; c++) {
+                const uint32_t j = arr[c];
+                if (j >= jlim) break;  // nearer candidates yield even less
+                if (sb[j] != tgt) continue;
                 const uint32_t cap = min(e - j, room);
                 uint32_t l = 3;
                 while (l < cap) {
@@ -371,12 +356,11 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
                 if (l > best) {
                     best = l;
                     boff = e - j;
+                    if (room <= best) break;
                     jlim = e - best;
                     sb = s + best;
                     tgt = s[e + best];
-                    if (room <= best) c = r;
                 }
-                c++;
             }
         }
         if (act) {
