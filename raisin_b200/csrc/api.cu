@@ -18,13 +18,13 @@ static cudaStream_t pick_stream(void *stream) { return stream ? (cudaStream_t)st
 static int to_host(uint8_t *d, size_t n, uint8_t **out, size_t *out_n, cudaStream_t s) {
     uint8_t *h = (uint8_t *)host_out_alloc(n ? n : 1);
     if (!h) {
-        cudaFreeAsync(d, s);
+        out_free(d, s);
         return RSN_ERR_NOMEM;
     }
     cudaError_t e = cudaSuccess;
     if (n) e = cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaFreeAsync(d, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    out_free(d, s);
     if (e != cudaSuccess) {
         rsn_free(h);
         return cuda_fail(e, "to_host", __FILE__, __LINE__);
@@ -77,7 +77,7 @@ static int layers_dev(const std::vector<Algo> &algos, bool compress, const uint8
         else
             rc = compress ? huff_compress_dev(cur, cur_n, &next, &next_n, s)
                           : huff_decompress_dev(cur, cur_n, nullptr, 0, &next, &next_n, s);
-        if (owned) cudaFreeAsync(owned, s);
+        if (owned) out_free(owned, s);
         owned = nullptr;
         if (rc != RSN_OK) return rc;
         owned = next;
@@ -99,6 +99,7 @@ int rsn_lzss_compress(const uint8_t *in, size_t n, int64_t window, int variant, 
     if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());
     cudaStream_t s = ctx().own_stream;
+    ArenaScope scope(s);
     DevBuf d;
     RSN_TRY(to_device(in, n, d, s));
     uint8_t *r = nullptr;
@@ -111,6 +112,7 @@ int rsn_lzss_decompress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_
     if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());
     cudaStream_t s = ctx().own_stream;
+    ArenaScope scope(s);
     DevBuf d;
     RSN_TRY(to_device(in, n, d, s));
     uint8_t *r = nullptr;
@@ -123,6 +125,7 @@ int rsn_huff_compress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_n)
     if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());
     cudaStream_t s = ctx().own_stream;
+    ArenaScope scope(s);
     DevBuf d;
     RSN_TRY(to_device(in, n, d, s));
     uint8_t *r = nullptr;
@@ -135,6 +138,7 @@ int rsn_huff_decompress(const uint8_t *in, size_t n, int strict_limits, uint8_t 
     if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());
     cudaStream_t s = ctx().own_stream;
+    ArenaScope scope(s);
     DevBuf d;
     RSN_TRY(to_device(in, n, d, s));
     uint8_t *r = nullptr;
@@ -150,6 +154,7 @@ static int layers_host(const char *algorithms, bool compress, const uint8_t *in,
     RSN_TRY(parse_layers(algorithms, algos));
     RSN_TRY(ensure_ctx());
     cudaStream_t s = ctx().own_stream;
+    ArenaScope scope(s);
     DevBuf d;
     RSN_TRY(to_device(in, n, d, s));
     uint8_t *r = nullptr;
@@ -220,6 +225,7 @@ int rsn_dev_lzss_match(const uint8_t *d_enc, size_t n, int64_t window, uint32_t 
     if (n == 0) return RSN_OK;
     uint32_t W = 0;
     RSN_TRY(lzss_effective_window(window, n, &W));
+    ArenaScope scope(pick_stream(stream));
     return finish(lzss_match(d_enc, n, W, d_packed, pick_stream(stream)), stream);
 }
 

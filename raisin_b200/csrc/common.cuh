@@ -45,16 +45,33 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         RSN_CUDA(cudaGetLastError());                                        \
     } while (0)
 
-// Stream-ordered device buffer; freed (stream-ordered) on scope exit unless released.
+// Device memory.  Temporaries of a call are bump-allocated from a per-thread arena that is
+// rewound when the call's ArenaScope ends (no driver call on the hot path); results handed back
+// to the caller come from a size-class cache of cudaMalloc'd buffers (rsn_dev_free returns them).
+// (cudaMallocAsync pools showed multi-millisecond, occasionally >100 ms, stalls here.)
+struct ArenaScope {
+    cudaStream_t s;
+    size_t saved_block, saved_off;
+    explicit ArenaScope(cudaStream_t stream);
+    ~ArenaScope();
+    ArenaScope(const ArenaScope &) = delete;
+    ArenaScope &operator=(const ArenaScope &) = delete;
+};
+void *arena_alloc(size_t n);
+void *out_alloc(size_t n, cudaStream_t s);
+void out_free(void *p, cudaStream_t s);
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     cudaStream_t s = nullptr;
+    bool is_out = false;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { reset(); }
-    int alloc(size_t n, cudaStream_t stream);
+    int alloc(size_t n, cudaStream_t stream);      // arena temporary (valid until the ArenaScope ends)
+    int alloc_out(size_t n, cudaStream_t stream);  // caller-visible result
     void reset();
     void *release() {
         void *q = p;
@@ -63,6 +80,17 @@ struct DevBuf {
     }
     template <typename T>
     T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Stage tracer: with RSN_TRACE=1 in the environment, prints host wall time between marks
+// (each mark synchronises the stream first, so it is for diagnosis only).
+struct Trace {
+    cudaStream_t s;
+    bool on;
+    double t0;
+    const char *what;
+    Trace(const char *w, cudaStream_t stream);
+    void mark(const char *label);
 };
 
 // ----------------------------------------------------------------------------- geometry

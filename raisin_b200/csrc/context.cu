@@ -2,7 +2,9 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -37,11 +39,6 @@ static int init_ctx(int device) {
     c.device = device;
     if (!c.own_stream) RSN_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     if (!c.h_scalars) RSN_CUDA(cudaHostAlloc((void **)&c.h_scalars, 64 * sizeof(uint64_t), cudaHostAllocDefault));
-    // keep stream-ordered allocations cached in the pool instead of returning them to the driver
-    cudaMemPool_t pool;
-    RSN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thresh = UINT64_MAX;
-    RSN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     c.ready = true;
     return RSN_OK;
 }
@@ -57,23 +54,239 @@ int ensure_ctx() {
     return init_ctx(-1);
 }
 
+// ----------------------------------------------------------------------------- arena
+
+namespace {
+struct ArenaBlock {
+    char *p;
+    size_t cap, off;
+};
+struct Arena {
+    std::vector<ArenaBlock> blocks;
+    size_t cur = 0;
+    int depth = 0;
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
+};
+thread_local Arena g_arena;
+
+constexpr size_t kArenaAlign = 256;
+constexpr size_t kArenaMinBlock = (size_t)64 << 20;
+
+void arena_free_all() {
+    for (auto &b : g_arena.blocks) cudaFree(b.p);
+    g_arena.blocks.clear();
+    g_arena.cur = 0;
+}
+}  // namespace
+
+void *arena_alloc(size_t n) {
+    Arena &a = g_arena;
+    n = (n + kArenaAlign - 1) & ~(kArenaAlign - 1);
+    if (n == 0) n = kArenaAlign;
+    for (; a.cur < a.blocks.size(); a.cur++) {
+        ArenaBlock &b = a.blocks[a.cur];
+        if (b.off + n <= b.cap) {
+            void *p = b.p + b.off;
+            b.off += n;
+            return p;
+        }
+        if (a.cur + 1 < a.blocks.size()) a.blocks[a.cur + 1].off = 0;
+    }
+    size_t total = 0;
+    for (auto &b : a.blocks) total += b.cap;
+    size_t cap = n > total ? n : total;  // at least double the arena
+    if (cap < kArenaMinBlock) cap = kArenaMinBlock;
+    char *p = nullptr;
+    if (cudaMalloc((void **)&p, cap) != cudaSuccess) {
+        cudaGetLastError();
+        if (cap == n || cudaMalloc((void **)&p, n) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        cap = n;
+    }
+    a.blocks.push_back(ArenaBlock{p, cap, n});
+    a.cur = a.blocks.size() - 1;
+    return p;
+}
+
+ArenaScope::ArenaScope(cudaStream_t stream) : s(stream) {
+    Arena &a = g_arena;
+    if (a.depth == 0) {
+        // the arena's previous user may still have work in flight on another stream
+        if (a.used && a.last_stream != stream) cudaStreamSynchronize(a.last_stream);
+        a.last_stream = stream;
+        a.used = true;
+        a.cur = 0;
+        if (!a.blocks.empty()) a.blocks[0].off = 0;
+    }
+    saved_block = a.cur;
+    saved_off = a.blocks.empty() ? 0 : a.blocks[a.cur].off;
+    a.depth++;
+}
+
+ArenaScope::~ArenaScope() {
+    Arena &a = g_arena;
+    a.depth--;
+    if (a.depth > 0) {
+        a.cur = saved_block;
+        if (!a.blocks.empty()) a.blocks[a.cur].off = saved_off;
+        return;
+    }
+    if (a.blocks.size() > 1) {
+        // the call outgrew the arena: replace the chain by one block so the next call fits in it
+        size_t total = 0;
+        for (auto &b : a.blocks) total += b.cap;
+        cudaStreamSynchronize(s);
+        arena_free_all();
+        char *p = nullptr;
+        total += total / 4;
+        if (cudaMalloc((void **)&p, total) == cudaSuccess) a.blocks.push_back(ArenaBlock{p, total, 0});
+        else cudaGetLastError();
+    }
+    a.cur = 0;
+    if (!a.blocks.empty()) a.blocks[0].off = 0;
+}
+
+// ----------------------------------------------------------------------------- result buffers
+
+namespace {
+struct OutCache {
+    std::mutex mu;
+    struct Ent {
+        size_t cap;
+        cudaStream_t last;
+    };
+    std::unordered_map<void *, Ent> live;
+    std::unordered_map<size_t, std::vector<std::pair<void *, cudaStream_t>>> free_;
+    size_t cached = 0;
+    static constexpr size_t kMaxCached = (size_t)16 << 30;
+
+    static size_t size_class(size_t n) {
+        if (n < 4096) return 4096;
+        size_t p2 = (size_t)1 << (63 - __builtin_clzll((unsigned long long)n));
+        size_t step = p2 / 8;
+        return (n + step - 1) / step * step;
+    }
+    void *get(size_t n, cudaStream_t s) {
+        const size_t c = size_class(n);
+        void *p = nullptr;
+        cudaStream_t last = nullptr;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_.find(c);
+            if (it != free_.end() && !it->second.empty()) {
+                p = it->second.back().first;
+                last = it->second.back().second;
+                it->second.pop_back();
+                cached -= c;
+                live[p] = Ent{c, s};
+            }
+        }
+        if (p) {
+            if (last != s) cudaStreamSynchronize(last);  // its previous user may still be reading it
+            return p;
+        }
+        if (cudaMalloc(&p, c) != cudaSuccess) {
+            cudaGetLastError();
+            drain();
+            if (cudaMalloc(&p, c) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        std::lock_guard<std::mutex> g(mu);
+        live[p] = Ent{c, s};
+        return p;
+    }
+    void put(void *p, cudaStream_t s) {
+        if (!p) return;
+        size_t c = 0;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = live.find(p);
+            if (it == live.end()) return;  // not ours
+            c = it->second.cap;
+            live.erase(it);
+            if (cached + c <= kMaxCached) {
+                free_[c].push_back({p, s});
+                cached += c;
+                return;
+            }
+        }
+        cudaStreamSynchronize(s);
+        cudaFree(p);
+    }
+    void drain() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &kv : free_)
+            for (auto &e : kv.second) cudaFree(e.first);
+        free_.clear();
+        cached = 0;
+    }
+};
+OutCache &outs() {
+    static OutCache *c = new OutCache();
+    return *c;
+}
+}  // namespace
+
+void *out_alloc(size_t n, cudaStream_t s) { return outs().get(n ? n : 1, s); }
+void out_free(void *p, cudaStream_t s) { outs().put(p, s); }
+
 int DevBuf::alloc(size_t n, cudaStream_t stream) {
     reset();
     s = stream;
+    is_out = false;
     bytes = n ? n : 1;
-    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
-    if (e != cudaSuccess) {
-        p = nullptr;
-        return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+    p = arena_alloc(bytes);
+    if (!p) {
+        snprintf(ctx().cuda_err, sizeof(ctx().cuda_err), "device arena: cannot allocate %zu bytes", bytes);
+        return RSN_ERR_NOMEM;
+    }
+    return RSN_OK;
+}
+
+int DevBuf::alloc_out(size_t n, cudaStream_t stream) {
+    reset();
+    s = stream;
+    is_out = true;
+    bytes = n ? n : 1;
+    p = out_alloc(bytes, stream);
+    if (!p) {
+        snprintf(ctx().cuda_err, sizeof(ctx().cuda_err), "device result buffer: cannot allocate %zu bytes", bytes);
+        return RSN_ERR_NOMEM;
     }
     return RSN_OK;
 }
 
 void DevBuf::reset() {
-    if (p) {
-        cudaFreeAsync(p, s);
-        p = nullptr;
+    if (p && is_out) out_free(p, s);  // arena temporaries are rewound by the ArenaScope
+    p = nullptr;
+}
+
+// ----------------------------------------------------------------------------- tracer
+
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+Trace::Trace(const char *w, cudaStream_t stream) : s(stream), what(w) {
+    static const bool enabled = getenv("RSN_TRACE") != nullptr;
+    on = enabled;
+    if (on) {
+        cudaStreamSynchronize(s);
+        t0 = now_ms();
     }
+}
+void Trace::mark(const char *label) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    const double t = now_ms();
+    fprintf(stderr, "[rsn trace] %-10s %-22s %8.3f ms\n", what, label, t - t0);
+    t0 = t;
 }
 
 // ----------------------------------------------------------------------------- spine scan
@@ -197,6 +410,8 @@ void rsn_shutdown(void) {
     }
     c.ready = false;
     rsn::pinned().drain();
+    rsn::arena_free_all();
+    rsn::outs().drain();
 }
 
 const char *rsn_strerror(int rc) {
@@ -228,7 +443,7 @@ void rsn_host_free(void *p) { rsn::pinned().put(p); }
 void rsn_dev_free(void *d_ptr, void *stream) {
     if (!d_ptr) return;
     cudaStream_t s = stream ? (cudaStream_t)stream : rsn::ctx().own_stream;
-    cudaFreeAsync(d_ptr, s);
+    rsn::out_free(d_ptr, s);
 }
 
 uint64_t rsn_kernel_launches(void) { return rsn::ctx().launches; }

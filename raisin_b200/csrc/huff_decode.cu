@@ -117,6 +117,7 @@ __global__ void k_hdec_write(DecParams p, size_t subs, const uint64_t *__restric
 
 int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int strict, uint8_t **d_out, size_t *out_n,
                         cudaStream_t s) {
+    ArenaScope scope(s);
     Ctx &c = ctx();
     // ---- host: find the first 5C 0A (strings.SplitN, huffman.go:261) and parse the header
     std::vector<uint8_t> h_copy;
@@ -178,7 +179,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
         if (max > 0) return RSN_ERR_SINGLE_LEAF_LOOP;
         uint8_t u[4];
         const int w = utf8_encode(rootn.right, u);
-        RSN_TRY(out.alloc(16, s));
+        RSN_TRY(out.alloc_out(16, s));
         RSN_CUDA(cudaMemcpyAsync(out.p, u, (size_t)w, cudaMemcpyHostToDevice, s));
         RSN_CUDA(cudaStreamSynchronize(s));
         *d_out = (uint8_t *)out.release();
@@ -221,7 +222,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
     RSN_TRY(spine_scan_u64(cnt.as<uint64_t>(), off.as<uint64_t>(), off.as<uint64_t>() + subs, subs, s));
     uint64_t total = 0;
     RSN_TRY(read_u64(off.as<uint64_t>() + subs, &total, s));
-    RSN_TRY(out.alloc(total + 16, s));
+    RSN_TRY(out.alloc_out(total + 16, s));
     RSN_CUDA(cudaMemsetAsync(flag.p, 0, 8, s));
     RSN_LAUNCH(k_hdec_write, grid, 128, 0, s, p, subs, start.as<uint64_t>(), off.as<uint64_t>(), out.as<uint8_t>(),
                flag.as<uint32_t>());

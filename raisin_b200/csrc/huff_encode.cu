@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(kTileThreads) k_enc_write(const uint8_t *__res
 // ============================================================================= host orchestration
 
 int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s) {
+    ArenaScope scope(s);
     if (n == 0) return RSN_ERR_EMPTY_INPUT;
     Ctx &c = ctx();
     const size_t tiles = div_up(n, kTile);
@@ -276,7 +277,7 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
 
     // ---- output buffer: zero, then header | 5C 0A | pad, then the bits
     DevBuf out;
-    RSN_TRY(out.alloc(total + 16, s));
+    RSN_TRY(out.alloc_out(total + 16, s));
     RSN_CUDA(cudaMemsetAsync(out.p, 0, total + 16, s));
     std::vector<uint8_t> pre(hdr);
     pre.push_back(0x5C);

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kTileThreads) k_unesc_apply(const uint8_t *__r
 static int lzss_unescape(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s) {
     DevBuf out;
     if (n == 0) {
-        RSN_TRY(out.alloc(16, s));
+        RSN_TRY(out.alloc_out(16, s));
         *d_out = (uint8_t *)out.release();
         *out_n = 0;
         return RSN_OK;
@@ -430,7 +430,7 @@ static int lzss_unescape(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t 
                toff.as<uint64_t>() + tiles);
     uint64_t total = 0;
     RSN_TRY(read_u64(toff.as<uint64_t>() + tiles, &total, s));
-    RSN_TRY(out.alloc(total + 16, s));
+    RSN_TRY(out.alloc_out(total + 16, s));
     RSN_LAUNCH(k_unesc_apply, (unsigned)tiles, kTileThreads, 0, s, d_in, n, tstate.as<uint8_t>(), toff.as<uint64_t>(),
                out.as<uint8_t>());
     *d_out = (uint8_t *)out.release();
@@ -441,8 +441,10 @@ static int lzss_unescape(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t 
 // ============================================================================= host orchestration
 
 int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s) {
+    ArenaScope scope(s);
     if (n == 0) return lzss_unescape(d_in, 0, d_out, out_n, s);
     const size_t tiles = div_up(n, kTile);
+    Trace tr("lzd", s);
     DevBuf tmap, tstate, st, tout, toff, err;
     RSN_TRY(tmap.alloc(tiles, s));
     RSN_TRY(tstate.alloc(tiles, s));
@@ -451,6 +453,7 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
     RSN_TRY(toff.alloc((tiles + 1) * 8, s));
     RSN_TRY(err.alloc(16, s));
     RSN_CUDA(cudaMemsetAsync(err.p, 0, 16, s));
+    tr.mark("alloc");
     RSN_LAUNCH(k_tok_reduce, (unsigned)tiles, kTileThreads, 0, s, d_in, n, tmap.as<uint8_t>());
     RSN_LAUNCH(k_tok_spine, 1, 1024, 0, s, tmap.as<uint8_t>(), tiles, tstate.as<uint8_t>());
     RSN_LAUNCH(k_tok_states, (unsigned)tiles, kTileThreads, 0, s, d_in, n, tstate.as<uint8_t>(), st.as<uint8_t>());
@@ -464,11 +467,14 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
     RSN_CUDA(cudaStreamSynchronize(s));
     if ((uint32_t)c.h_scalars[0] & ERR_BAD_REF) return RSN_ERR_BAD_REFERENCE;
     if (sbn >= (1ull << 32)) return RSN_ERR_UNSUPPORTED;  // u32 source distances (documented limit)
+    tr.mark("states+sizes");
     DevBuf sb, dist;
     RSN_TRY(sb.alloc(sbn + 16, s));
     RSN_TRY(dist.alloc(sbn * 4 + 16, s));
+    tr.mark("alloc sb/dist");
     RSN_LAUNCH(k_tok_scatter, (unsigned)tiles, kTileThreads, 0, s, d_in, st.as<uint8_t>(), n, toff.as<uint64_t>(),
                sb.as<uint8_t>(), dist.as<uint32_t>(), err.as<uint32_t>());
+    tr.mark("scatter");
     if (sbn) {
         uint32_t *unfinished = err.as<uint32_t>() + 1;
         for (int round = 0; round < 64; round++) {
@@ -482,9 +488,12 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
             if (!u) break;
         }
     }
+    tr.mark("resolve");
     st.reset();
     dist.reset();
-    return lzss_unescape(sb.as<uint8_t>(), (size_t)sbn, d_out, out_n, s);
+    const int rc = lzss_unescape(sb.as<uint8_t>(), (size_t)sbn, d_out, out_n, s);
+    tr.mark("unescape");
+    return rc;
 }
 
 }  // namespace rsn

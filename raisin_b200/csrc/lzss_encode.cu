@@ -551,7 +551,7 @@ static int parse_and_emit(const uint8_t *d_enc, size_t n, ParseCfg cfg, const ui
     uint64_t total = 0;
     RSN_TRY(read_u64(bo.as<uint64_t>() + blocks, &total, s));
     DevBuf out;
-    RSN_TRY(out.alloc(total + 16, s));
+    RSN_TRY(out.alloc_out(total + 16, s));
     RSN_LAUNCH(k_emit_write, (unsigned)blocks, kPT, 0, s, cfg, d_enc, d_lo, n, vis.as<uint16_t>(), bo.as<uint64_t>(),
                out.as<uint8_t>());
     *d_out = (uint8_t *)out.release();
@@ -571,6 +571,7 @@ int lzss_effective_window(int64_t window, size_t enc_n, uint32_t *W) {
 
 int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant, uint8_t **d_out, size_t *out_n,
                       cudaStream_t s) {
+    ArenaScope scope(s);
     if (variant != RSN_LZSS_ASYNC && variant != RSN_LZSS_ITER) return RSN_ERR_INVALID_ARG;
     DevBuf enc_buf;
     const uint8_t *enc = nullptr;
@@ -578,7 +579,7 @@ int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant
     RSN_TRY(lzss_escape(d_in, n, enc_buf, &enc, &en, s));
     if (en == 0) {
         DevBuf out;
-        RSN_TRY(out.alloc(16, s));
+        RSN_TRY(out.alloc_out(16, s));
         *d_out = (uint8_t *)out.release();
         *out_n = 0;
         return RSN_OK;
