@@ -257,6 +257,30 @@ def main():
 
     dec_ms = statistics.mean(timed(dec_only, max(3, args.steps // 2), 1))
 
+    # ---- Huffman layer on the same stream (BASELINE configs[0]/[2] use it): encode/decode of the
+    # LZSS output, device resident
+    hk = {}
+
+    def henc_only():
+        o = C.c_void_p()
+        on = C.c_size_t()
+        rsn._lib.check(lib.rsn_dev_huff_compress(keep["c"], keep["cn"], C.byref(o), C.byref(on), sptr))
+        if "h" in hk:
+            lib.rsn_dev_free(hk["h"], sptr)
+        hk["h"], hk["hn"] = o, on.value
+        return None
+
+    henc_ms = statistics.mean(timed(henc_only, max(3, args.steps // 2), 2))
+
+    def hdec_only():
+        o = C.c_void_p()
+        on = C.c_size_t()
+        rsn._lib.check(lib.rsn_dev_huff_decompress(hk["h"], hk["hn"], 0, C.byref(o), C.byref(on), sptr))
+        lib.rsn_dev_free(o, sptr)
+        return None
+
+    hdec_ms = statistics.mean(timed(hdec_only, max(3, args.steps // 2), 2))
+
     # ---- dominant kernel (K2 match search) alone, CUDA events on its launch stream
     # the text stream has no '<', '\\' or 0xFF bytes, so the escaped buffer equals the raw one
     d_packed = torch.empty(n, dtype=torch.int32, device="cuda")
@@ -294,9 +318,9 @@ def main():
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e, enc_ms, dec_ms, k2_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e, enc_ms, dec_ms, k2_ms, henc_ms, hdec_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e, enc_ms, dec_ms, k2_ms = t.tolist()
+        ms, e2e, enc_ms, dec_ms, k2_ms, henc_ms, hdec_ms = t.tolist()
 
     peak, peak_src = peaks()
     algo_bytes_k2 = n + keep["cn"]  # LZSS compress = n + c per stream; one K2 launch = one stream
@@ -310,6 +334,11 @@ def main():
                    "l2": "flushed between timed iterations (256 MiB write)"},
         "encode_GBps": world * n / (enc_ms * 1e-3) / 1e9, "decode_GBps": world * n / (dec_ms * 1e-3) / 1e9,
         "compressed_bytes": keep["cn"],
+        "huffman_layer": {"input_bytes": keep["cn"], "output_bytes": hk["hn"],
+                          "encode_GBps": world * keep["cn"] / (henc_ms * 1e-3) / 1e9,
+                          "decode_GBps": world * keep["cn"] / (hdec_ms * 1e-3) / 1e9,
+                          "layered_encode_GBps": world * n / ((enc_ms + henc_ms) * 1e-3) / 1e9,
+                          "layered_decode_GBps": world * n / ((dec_ms + hdec_ms) * 1e-3) / 1e9},
         "e2e": {"value": world * n / (e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e},
         "gpu_launches": launches,

@@ -291,8 +291,15 @@ void Trace::mark(const char *label) {
 
 // ----------------------------------------------------------------------------- spine scan
 
-__global__ void __launch_bounds__(1024) k_spine_scan_u64(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
-                                                         uint64_t *__restrict__ total, size_t count) {
+// Exclusive scan of u64 values.  Small inputs: one CTA.  Large inputs: per-chunk totals, a
+// recursive scan of those, then a per-chunk scan seeded with its offset.
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_single(const uint64_t *__restrict__ in,
+                                                               uint64_t *__restrict__ out,
+                                                               uint64_t *__restrict__ total, size_t count) {
     __shared__ uint64_t sm[33];
     uint64_t carry = 0;
     for (size_t base = 0; base < count; base += blockDim.x) {
@@ -306,8 +313,52 @@ __global__ void __launch_bounds__(1024) k_spine_scan_u64(const uint64_t *__restr
     if (threadIdx.x == 0 && total) *total = carry;
 }
 
+__global__ void __launch_bounds__(kScanThreads) k_scan_chunk_totals(const uint64_t *__restrict__ in, size_t count,
+                                                                     uint64_t *__restrict__ chunk_tot) {
+    __shared__ uint64_t sm[33];
+    const size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
+    uint64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++)
+        if (base + k < count) v += in[base + k];
+    uint64_t tot;
+    block_exclusive_sum<uint64_t>(v, sm, tot);
+    if (threadIdx.x == 0) chunk_tot[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_chunks(const uint64_t *__restrict__ in, size_t count,
+                                                               const uint64_t *__restrict__ chunk_off,
+                                                               uint64_t *__restrict__ out) {
+    __shared__ uint64_t sm[33];
+    const size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
+    uint64_t x[kScanItems];
+    uint64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        x[k] = base + k < count ? in[base + k] : 0;
+        v += x[k];
+    }
+    uint64_t tot;
+    uint64_t run = chunk_off[blockIdx.x] + block_exclusive_sum<uint64_t>(v, sm, tot);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < count) out[base + k] = run;
+        run += x[k];
+    }
+}
+
 int spine_scan_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t *d_total, size_t count, cudaStream_t s) {
-    RSN_LAUNCH(k_spine_scan_u64, 1, 1024, 0, s, d_in, d_out, d_total, count);
+    if (count <= (size_t)kScanChunk * 2) {
+        RSN_LAUNCH(k_scan_single, 1, kScanThreads, 0, s, d_in, d_out, d_total, count);
+        return RSN_OK;
+    }
+    const size_t chunks = div_up(count, kScanChunk);
+    DevBuf tot, off;
+    RSN_TRY(tot.alloc(chunks * 8, s));
+    RSN_TRY(off.alloc(chunks * 8, s));
+    RSN_LAUNCH(k_scan_chunk_totals, (unsigned)chunks, kScanThreads, 0, s, d_in, count, tot.as<uint64_t>());
+    RSN_TRY(spine_scan_u64(tot.as<uint64_t>(), off.as<uint64_t>(), d_total, chunks, s));
+    RSN_LAUNCH(k_scan_chunks, (unsigned)chunks, kScanThreads, 0, s, d_in, count, off.as<uint64_t>(), d_out);
     return RSN_OK;
 }
 
