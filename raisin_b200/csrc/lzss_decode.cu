@@ -178,12 +178,16 @@ __device__ __forceinline__ void parse_token(const uint8_t *__restrict__ in, cons
     cnt = go_atoi_dev(in, j + 1, i);
 }
 
-enum : uint32_t { ERR_BAD_REF = 1u, ERR_TOO_BIG = 2u };
+enum : uint32_t { ERR_BAD_REF = 1u, FLAG_NEEDS_UNESCAPE = 2u };
 
 // out-size contribution of byte i (literal: 1, closing '>': cnt, else 0)
 __device__ __forceinline__ uint64_t tok_contrib(const uint8_t *__restrict__ in, const uint8_t *__restrict__ st,
                                                 size_t i, uint8_t b, uint8_t s, uint32_t *err) {
-    if (s == ST_OPEN) return b == 0x3C ? 0 : 1;
+    if (s == ST_OPEN) {
+        if (b == 0x3C) return 0;
+        if (err && (b == 0x5C || b == 0xFF)) atomicOr(err, FLAG_NEEDS_UNESCAPE);  // rare bytes
+        return 1;
+    }
     if (s == ST_CLOSE && b == 0x3E) {
         int64_t ptr, cnt;
         parse_token(in, st, i, ptr, cnt);
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tok_scatter(const uint8_t *__r
 
 // ============================================================================= K6 resolve
 
-constexpr int kHops = 32;
+constexpr int kHops = 64;
 
 // Every referenced byte follows its source chain to a literal.  Chains longer than kHops are
 // shortened in place (dist[o] := distance to the furthest ancestor reached) and finished by a
@@ -280,7 +284,8 @@ __global__ void __launch_bounds__(256) k_resolve(uint8_t *__restrict__ sb, uint3
     size_t p = o - d;
     int hops = 0;
     uint32_t dp;
-    while ((dp = ((volatile uint32_t *)dist)[p]) != 0 && hops < kHops) {
+    // plain (L1-cacheable) loads: a stale distance still names a true ancestor
+    while ((dp = dist[p]) != 0 && hops < kHops) {
         p -= dp;
         hops++;
     }
@@ -468,8 +473,9 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
     if ((uint32_t)c.h_scalars[0] & ERR_BAD_REF) return RSN_ERR_BAD_REFERENCE;
     if (sbn >= (1ull << 32)) return RSN_ERR_UNSUPPORTED;  // u32 source distances (documented limit)
     tr.mark("states+sizes");
-    DevBuf sb, dist;
-    RSN_TRY(sb.alloc(sbn + 16, s));
+    const bool needs_unescape = ((uint32_t)c.h_scalars[0] & FLAG_NEEDS_UNESCAPE) != 0;
+    DevBuf sb, dist;  // sb becomes the result itself when no literal needs un-escaping
+    RSN_TRY(sb.alloc_out(sbn + 16, s));
     RSN_TRY(dist.alloc(sbn * 4 + 16, s));
     tr.mark("alloc sb/dist");
     RSN_LAUNCH(k_tok_scatter, (unsigned)tiles, kTileThreads, 0, s, d_in, st.as<uint8_t>(), n, toff.as<uint64_t>(),
@@ -489,8 +495,11 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
         }
     }
     tr.mark("resolve");
-    st.reset();
-    dist.reset();
+    if (!needs_unescape) {  // no 0x5C / 0xFF among the literals: the buffer is already the answer
+        *d_out = (uint8_t *)sb.release();
+        *out_n = (size_t)sbn;
+        return RSN_OK;
+    }
     const int rc = lzss_unescape(sb.as<uint8_t>(), (size_t)sbn, d_out, out_n, s);
     tr.mark("unescape");
     return rc;
