@@ -35,9 +35,9 @@ struct Smem {
     uint32_t s_words[SLEN / 4 + 4];   // staged bytes: [base, base + avail), zero padded
     uint16_t a[ECAP];                 // ping
     uint16_t b[ECAP];                 // pong
-    uint16_t cnt[256 * WARPS];        // [digit][warp]
+    alignas(16) uint16_t ctr[16 * THREADS];  // radix: [digit][thread]; later: work-class counters
     uint32_t heads[ECAP / 32 + 2];    // bit r: slot r starts a 3-gram group
-    uint8_t info[ECAP];               // per slot: rank inside its (chunk, digit) group | 0x80 if last of it
+    uint8_t info[ECAP];               // per slot: work class of its candidate list
     uint8_t lowL[T];                  // 0..3 from the 1/2/3-gram stages, 0xFF once the final result is written
     uint32_t scan[33];
     uint32_t wtot[WARPS + 1];
@@ -50,84 +50,59 @@ __device__ __forceinline__ uint32_t lds32(const uint8_t *s, uint32_t pos) {
     return __funnelshift_r(lo, hi, (pos & 3u) * 8);
 }
 
-// lanes with the same 8-bit digit as mine (among `active` lanes)
-__device__ __forceinline__ unsigned same_digit(uint32_t digit, unsigned active) {
-    unsigned peers = active;
+// One stable counting pass on the 4-bit digit (s[e + byteoff] >> shift) & 15 from src to dst over
+// slots [0, ev).  Thread t owns the contiguous slots [t*per, (t+1)*per) and a private column of
+// 16 digit counters ctr[digit][t] (plain shared-memory increments, no atomics, no ballots); one
+// block-wide exclusive scan over the counters in (digit, thread) order turns them into stable
+// destinations.  Two passes (low nibble, high nibble) sort by one byte.
+__device__ __forceinline__ void radix_pass4(Smem &sm, const uint8_t *s, const uint16_t *src, uint16_t *dst,
+                                            uint32_t ev, uint32_t byteoff, uint32_t shift) {
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (ev + THREADS - 1) / THREADS;
+    const uint32_t lo = min(ev, t * per), hi = min(ev, lo + per);
+    uint16_t *col = sm.ctr + t;
 #pragma unroll
-    for (int bit = 0; bit < 8; bit++) {
-        const unsigned m = __ballot_sync(0xffffffffu, (digit >> bit) & 1u);
-        peers &= ((digit >> bit) & 1u) ? m : ~m;
-    }
-    return peers;
-}
-
-// One stable counting pass on byte s[e + byteoff] from src to dst over slots [0, ev).
-// Warp w owns the contiguous slots [w*per, (w+1)*per): counters are (digit, warp) so the exclusive
-// scan in that order yields stable destinations without atomics.
-__device__ __forceinline__ void radix_pass(Smem &sm, const uint8_t *s, const uint16_t *src, uint16_t *dst,
-                                           uint32_t ev, uint32_t byteoff) {
-    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1;
-    const uint32_t per = ((ev + WARPS - 1) / WARPS + 31) & ~31u;  // slots per warp, multiple of 32
-    const uint32_t lo = min(ev, w * per), hi = min(ev, lo + per);
-    for (int i = threadIdx.x; i < 256 * WARPS; i += THREADS) sm.cnt[i] = 0;
-    __syncthreads();
-    // count (and remember each slot's rank inside its 32-slot digit group)
-    for (uint32_t c = lo; c < hi; c += 32) {
-        const uint32_t slot = c + lane;
-        const bool act = slot < hi;
-        const uint32_t e = act ? src[slot] : 0;
-        const uint32_t digit = act ? s[e + byteoff] : 0;
-        const unsigned active = __ballot_sync(0xffffffffu, act);
-        const unsigned peers = same_digit(digit, active);
-        if (act) {
-            const uint32_t rank = __popc(peers & lt);
-            const bool last = (peers >> lane) == 1u;
-            sm.info[slot] = (uint8_t)(rank | (last ? 0x80u : 0u));
-            if (last) sm.cnt[digit * WARPS + w] += (uint16_t)(rank + 1);
-        }
-        __syncwarp();
+    for (int d = 0; d < 16; d++) col[d * THREADS] = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t d = (s[src[i] + byteoff] >> shift) & 15u;
+        col[d * THREADS]++;
     }
     __syncthreads();
-    // exclusive scan of cnt in (digit, warp) order: 256*WARPS values, 8 per thread
     {
-        constexpr int PER = 256 * WARPS / THREADS;
-        uint32_t v[PER];
+        // thread t scans the 16 consecutive counters [16t, 16t+16) of the linear (digit, thread) order
+        uint4 *p = reinterpret_cast<uint4 *>(sm.ctr + t * 16);
+        uint4 q0 = p[0], q1 = p[1];
+        uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         uint32_t sum = 0;
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            v[k] = sm.cnt[threadIdx.x * PER + k];
-            sum += v[k];
-        }
+        for (int k = 0; k < 8; k++) sum += (w[k] & 0xFFFFu) + (w[k] >> 16);
         uint32_t total;
         uint32_t run = block_exclusive_sum<uint32_t>(sum, sm.scan, total);
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            sm.cnt[threadIdx.x * PER + k] = (uint16_t)run;
-            run += v[k];
+        for (int k = 0; k < 8; k++) {
+            const uint32_t a = w[k] & 0xFFFFu, b2 = w[k] >> 16;
+            w[k] = run | ((run + a) << 16);
+            run += a + b2;
         }
+        p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        p[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
     __syncthreads();
-    // scatter
-    for (uint32_t c = lo; c < hi; c += 32) {
-        const uint32_t slot = c + lane;
-        const bool act = slot < hi;
-        uint32_t e = 0, digit = 0, inf = 0, basev = 0;
-        if (act) {
-            e = src[slot];
-            digit = s[e + byteoff];
-            inf = sm.info[slot];
-            basev = sm.cnt[digit * WARPS + w];
-        }
-        __syncwarp();
-        if (act) {
-            const uint32_t rank = inf & 0x7Fu;
-            dst[basev + rank] = (uint16_t)e;
-            if (inf & 0x80u) sm.cnt[digit * WARPS + w] = (uint16_t)(basev + rank + 1);
-        }
-        __syncwarp();
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t e = src[i];
+        const uint32_t d = (s[e + byteoff] >> shift) & 15u;
+        const uint32_t pos = col[d * THREADS];
+        col[d * THREADS] = (uint16_t)(pos + 1);
+        dst[pos] = (uint16_t)e;
     }
     __syncthreads();
+}
+
+// stable sort by the byte s[e + byteoff]: src -> (tmp) -> src; returns with the result in src
+__device__ __forceinline__ void radix_byte(Smem &sm, const uint8_t *s, uint16_t *src, uint16_t *tmp, uint32_t ev,
+                                           uint32_t byteoff) {
+    radix_pass4(sm, s, src, tmp, ev, byteoff, 0);
+    radix_pass4(sm, s, tmp, src, ev, byteoff, 4);
 }
 
 // Candidates of the sorted slot r (entry e): the slots [lo, r) of its 3-gram group whose positions
@@ -200,17 +175,17 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
     __syncthreads();
 
     // ---- pass 1: by enc[e+2]  ->  1-byte matches of q = e+2
-    radix_pass(sm, s, sm.a, sm.b, ev, 2);
+    radix_byte(sm, s, sm.a, sm.b, ev, 2);
     for (uint32_t r = threadIdx.x; r < ev; r += THREADS) {
-        const uint32_t e = sm.b[r], q = e + 2;
+        const uint32_t e = sm.a[r], q = e + 2;
         if (q >= halo && q < halo + tile_len && r > 0) {
-            const uint32_t p = sm.b[r - 1];
+            const uint32_t p = sm.a[r - 1];
             if (s[p + 2] == s[q] && e - p <= W) sm.lowL[q - halo] = 1;
         }
     }
     __syncthreads();
     // ---- pass 2: by (enc[e+1], enc[e+2])  ->  2-byte matches of q = e+1 at distance >= 2
-    radix_pass(sm, s, sm.b, sm.a, ev, 1);
+    radix_byte(sm, s, sm.a, sm.b, ev, 1);
     for (uint32_t r = threadIdx.x; r < ev; r += THREADS) {
         const uint32_t e = sm.a[r], q = e + 1;
         if (q >= halo && q < halo + tile_len) {
@@ -230,9 +205,9 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
     }
     __syncthreads();
     // ---- pass 3: by the 3-gram  ->  candidate lists in position order
-    radix_pass(sm, s, sm.a, sm.b, ev, 0);
-    const uint16_t *arr = sm.b;  // sorted by (3-gram, position)
-    uint16_t *order = sm.a;      // spare buffer: tile slots that have candidates, grouped by work class
+    radix_byte(sm, s, sm.a, sm.b, ev, 0);
+    const uint16_t *arr = sm.a;  // sorted by (3-gram, position)
+    uint16_t *order = sm.b;      // spare buffer: tile slots that have candidates, grouped by work class
     // ---- group heads
     {
         const uint32_t per = ((ev + WARPS - 1) / WARPS + 31) & ~31u;
@@ -245,7 +220,7 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
             if (lane == 0) sm.heads[c >> 5] = hm;
         }
     }
-    for (int i = threadIdx.x; i < 16 * WARPS; i += THREADS) sm.cnt[i] = 0;
+    for (int i = threadIdx.x; i < 16 * WARPS; i += THREADS) sm.ctr[i] = 0;
     __syncthreads();
     // ---- per tile slot: candidate range, work class.  Slots without candidates are final here.
     // Lanes of a warp later take slots of ONE class (similar candidate counts), which is what keeps
@@ -288,12 +263,12 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
                     const uint32_t rank = __popc(peers & lt);
                     const bool last = (peers >> lane) == 1u;
                     if (phase == 0) {
-                        if (last) sm.cnt[cls * WARPS + w] += (uint16_t)(rank + 1);
+                        if (last) sm.ctr[cls * WARPS + w] += (uint16_t)(rank + 1);
                     } else {
-                        const uint32_t basev = sm.cnt[cls * WARPS + w];
+                        const uint32_t basev = sm.ctr[cls * WARPS + w];
                         order[basev + rank] = (uint16_t)r;
                         __syncwarp(peers);
-                        if (last) sm.cnt[cls * WARPS + w] = (uint16_t)(basev + rank + 1);
+                        if (last) sm.ctr[cls * WARPS + w] = (uint16_t)(basev + rank + 1);
                     }
                 }
                 __syncwarp();
@@ -303,8 +278,8 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
                 if (threadIdx.x == 0) {  // exclusive scan of the 8 x WARPS class counters, class-major
                     uint32_t run = 0;
                     for (int k = 0; k < 8 * WARPS; k++) {
-                        const uint32_t v = sm.cnt[k];
-                        sm.cnt[k] = (uint16_t)run;
+                        const uint32_t v = sm.ctr[k];
+                        sm.ctr[k] = (uint16_t)run;
                         run += v;
                     }
                     sm.wtot[0] = run;
