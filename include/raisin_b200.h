@@ -113,6 +113,17 @@ int rsn_dev_upload(const void *h_src, size_t n, void *d_dst, void *stream);
  */
 int rsn_dev_lzss_match(const uint8_t *d_enc, size_t n, int64_t window, uint32_t *d_packed, void *stream);
 
+/*
+ * Second half of variant A/B compression from precomputed match arrays (the sequential merge
+ * of lzss.go:134-151 / 240-311): d_packed[i] as produced by rsn_dev_lzss_match over the same
+ * already-escaped buffer.  Used by the position-range sharded path after the arrays of all
+ * shards have been gathered.
+ */
+int rsn_dev_lzss_emit(const uint8_t *d_enc, size_t n, int64_t window, int variant, const uint32_t *d_packed,
+                      uint8_t **d_out, size_t *out_n, void *stream);
+/* EncodeOpeningSymbols (lzss.go:369-389) alone: the escaped buffer the match arrays refer to. */
+int rsn_dev_lzss_escape(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, void *stream);
+
 /* ---- introspection ----------------------------------------------------------------------- */
 
 /* Number of kernels this library has launched from the calling thread since the last reset. */

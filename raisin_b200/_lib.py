@@ -17,7 +17,7 @@ EXPORTS = [
     "rsn_host_free", "rsn_lzss_compress", "rsn_lzss_decompress", "rsn_huff_compress", "rsn_huff_decompress",
     "rsn_compress_layers", "rsn_decompress_layers", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
     "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_free", "rsn_dev_download", "rsn_dev_upload",
-    "rsn_dev_lzss_match",
+    "rsn_dev_lzss_match", "rsn_dev_lzss_emit", "rsn_dev_lzss_escape",
     "rsn_kernel_launches", "rsn_reset_kernel_launches", "rsn_version",
 ]
 
@@ -77,10 +77,12 @@ def lib():
     L.rsn_dev_free.restype = None
     L.rsn_dev_download.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.rsn_dev_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.rsn_dev_lzss_emit.argtypes = [C.c_void_p, C.c_size_t, C.c_int64, C.c_int, C.c_void_p, vpp, szp, C.c_void_p]
+    L.rsn_dev_lzss_escape.argtypes = [C.c_void_p, C.c_size_t, vpp, szp, C.c_void_p]
     L.rsn_dev_lzss_match.argtypes = [C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p]
     for name in ("rsn_lzss_compress", "rsn_lzss_decompress", "rsn_huff_compress", "rsn_huff_decompress",
                  "rsn_compress_layers", "rsn_decompress_layers", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
-                 "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_lzss_match", "rsn_dev_download",
+                 "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_lzss_match", "rsn_dev_lzss_emit", "rsn_dev_lzss_escape", "rsn_dev_download",
                  "rsn_dev_upload"):
         getattr(L, name).restype = C.c_int
     L.rsn_kernel_launches.argtypes = []

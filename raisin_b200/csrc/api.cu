@@ -204,6 +204,18 @@ int rsn_dev_huff_decompress(const uint8_t *d_in, size_t n, int strict_limits, ui
     return finish(huff_decompress_dev(d_in, n, nullptr, strict_limits, d_out, out_n, pick_stream(stream)), stream);
 }
 
+int rsn_dev_lzss_emit(const uint8_t *d_enc, size_t n, int64_t window, int variant, const uint32_t *d_packed,
+                      uint8_t **d_out, size_t *out_n, void *stream) {
+    if ((!d_enc && n) || (!d_packed && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    return finish(lzss_emit_dev(d_enc, n, window, variant, d_packed, d_out, out_n, pick_stream(stream)), stream);
+}
+int rsn_dev_lzss_escape(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, void *stream) {
+    if ((!d_in && n) || !d_out || !out_n) return RSN_ERR_INVALID_ARG;
+    RSN_TRY(ensure_ctx());
+    return finish(lzss_escape_dev(d_in, n, d_out, out_n, pick_stream(stream)), stream);
+}
+
 int rsn_dev_download(const void *d_src, size_t n, void *h_dst, void *stream) {
     RSN_TRY(ensure_ctx());
     cudaStream_t s = pick_stream(stream);

@@ -16,6 +16,9 @@ int lzss_effective_window(int64_t window, size_t enc_n, uint32_t *W);
 int lzss_escape(const uint8_t *d_in, size_t n, DevBuf &enc, const uint8_t **enc_ptr, size_t *enc_n, cudaStream_t s);
 int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant, uint8_t **d_out, size_t *out_n,
                       cudaStream_t s);
+int lzss_emit_dev(const uint8_t *d_enc, size_t n, int64_t window, int variant, const uint32_t *d_packed,
+                  uint8_t **d_out, size_t *out_n, cudaStream_t s);
+int lzss_escape_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s);
 int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s);
 
 }  // namespace rsn

@@ -569,6 +569,55 @@ int lzss_effective_window(int64_t window, size_t enc_n, uint32_t *W) {
     return RSN_OK;
 }
 
+// parse + emit over caller-provided match arrays (enc must be the escaped buffer they refer to)
+int lzss_emit_dev(const uint8_t *d_enc, size_t n, int64_t window, int variant, const uint32_t *d_packed,
+                  uint8_t **d_out, size_t *out_n, cudaStream_t s) {
+    if (variant != RSN_LZSS_ASYNC && variant != RSN_LZSS_ITER) return RSN_ERR_INVALID_ARG;
+    ArenaScope scope(s);
+    if (n == 0) {
+        DevBuf out;
+        RSN_TRY(out.alloc_out(16, s));
+        *d_out = (uint8_t *)out.release();
+        *out_n = 0;
+        return RSN_OK;
+    }
+    uint32_t W = 0;
+    RSN_TRY(lzss_effective_window(window, n, &W));
+    // the parse kernels read whole 4096-position blocks of the arrays: work on a padded copy
+    DevBuf lo, sbits, fp;
+    const size_t padded = div_up(n, kPB) * kPB;
+    RSN_TRY(lo.alloc(padded * 4 + 64, s));
+    RSN_CUDA(cudaMemcpyAsync(lo.p, d_packed, n * 4, cudaMemcpyDeviceToDevice, s));
+    ParseCfg cfg{W, W, variant, nullptr};
+    if (variant == RSN_LZSS_ITER) {
+        cfg.J = W + 1;
+        RSN_TRY(fp.alloc(512 * 8, s));
+        const size_t sb_bytes = (padded / 32 + 4) * 4;
+        RSN_TRY(sbits.alloc(sb_bytes, s));
+        RSN_CUDA(cudaMemsetAsync(sbits.p, 0, sb_bytes, s));
+        RSN_CUDA(cudaMemsetAsync(fp.p, 0xFF, 512 * 8, s));
+        RSN_LAUNCH(k_first_pos, (unsigned)div_up(n, 8192), 256, 0, s, d_enc, n, fp.as<unsigned long long>());
+        RSN_LAUNCH(k_start_bits, (unsigned)div_up(n + 31, 256), 256, 0, s, d_enc, n, fp.as<unsigned long long>(),
+                   sbits.as<uint32_t>());
+        cfg.sbits = sbits.as<uint32_t>();
+    }
+    return parse_and_emit(d_enc, n, cfg, lo.as<uint32_t>(), d_out, out_n, s);
+}
+
+int lzss_escape_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s) {
+    ArenaScope scope(s);
+    DevBuf enc_buf, out;
+    const uint8_t *enc = nullptr;
+    size_t en = 0;
+    RSN_TRY(lzss_escape(d_in, n, enc_buf, &enc, &en, s));
+    RSN_TRY(out.alloc_out(en + 64, s));
+    if (en) RSN_CUDA(cudaMemcpyAsync(out.p, enc, en, cudaMemcpyDeviceToDevice, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    *d_out = (uint8_t *)out.release();
+    *out_n = en;
+    return RSN_OK;
+}
+
 int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant, uint8_t **d_out, size_t *out_n,
                       cudaStream_t s) {
     ArenaScope scope(s);

@@ -61,11 +61,20 @@ __device__ __forceinline__ void radix_pass4(Smem &sm, const uint8_t *s, const ui
     const uint32_t per = (ev + THREADS - 1) / THREADS;
     const uint32_t lo = min(ev, t * per), hi = min(ev, lo + per);
     uint16_t *col = sm.ctr + t;
-#pragma unroll
-    for (int d = 0; d < 16; d++) col[d * THREADS] = 0;
+    // digit counts of my slots in two packed registers (16 x 8-bit fields; a thread owns <= 255 slots),
+    // so the loop is independent loads + register arithmetic with no shared-memory read-modify-write
+    uint64_t acc0 = 0, acc1 = 0;
+#pragma unroll 5
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t d = (s[src[i] + byteoff] >> shift) & 15u;
-        col[d * THREADS]++;
+        const uint64_t inc = 1ull << ((d & 7u) * 8);
+        acc0 += d < 8 ? inc : 0ull;
+        acc1 += d < 8 ? 0ull : inc;
+    }
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        col[d * THREADS] = (uint16_t)((acc0 >> (8 * d)) & 0xFFu);
+        col[(d + 8) * THREADS] = (uint16_t)((acc1 >> (8 * d)) & 0xFFu);
     }
     __syncthreads();
     {
@@ -88,12 +97,18 @@ __device__ __forceinline__ void radix_pass4(Smem &sm, const uint8_t *s, const ui
         p[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
     __syncthreads();
+    acc0 = 0;
+    acc1 = 0;
+#pragma unroll 5
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t e = src[i];
         const uint32_t d = (s[e + byteoff] >> shift) & 15u;
-        const uint32_t pos = col[d * THREADS];
-        col[d * THREADS] = (uint16_t)(pos + 1);
-        dst[pos] = (uint16_t)e;
+        const uint32_t sh = (d & 7u) * 8;
+        const uint32_t rank = (uint32_t)(((d < 8 ? acc0 : acc1) >> sh) & 0xFFu);  // earlier slots of mine, same digit
+        const uint64_t inc = 1ull << sh;
+        acc0 += d < 8 ? inc : 0ull;
+        acc1 += d < 8 ? 0ull : inc;
+        dst[col[d * THREADS] + rank] = (uint16_t)e;
     }
     __syncthreads();
 }
