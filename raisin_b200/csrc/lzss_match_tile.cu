@@ -41,6 +41,10 @@ struct Smem {
     uint8_t lowL[T];                  // 0..3 from the 1/2/3-gram stages, 0xFF once the final result is written
     uint32_t scan[33];
     uint32_t wtot[WARPS + 1];
+    // Diagonal cache for long matches: entry = (d << 32) | (start << 16) | end records that
+    // s[x] == s[x - d] for every staged x in [start, end).  Entries are only ever written after the
+    // bytes were compared, the data never changes, so any entry read (even a racing one) is true.
+    unsigned long long diag[16 * 8];  // 16 sets (d & 15) x 8 ways
 };
 
 __device__ __forceinline__ uint32_t lds32(const uint8_t *s, uint32_t pos) {
@@ -118,6 +122,49 @@ __device__ __forceinline__ void radix_byte(Smem &sm, const uint8_t *s, uint16_t 
                                            uint32_t byteoff) {
     radix_pass4(sm, s, src, tmp, ev, byteoff, 0);
     radix_pass4(sm, s, tmp, src, ev, byteoff, 4);
+}
+
+// Continuation of a match that is already 32+ bytes long: compare on, but consult and feed the
+// diagonal cache so that the thousands of positions of a tile that sit on the same long diagonal
+// run (highly repetitive data) do not each re-compare it.  Returns the (uncapped) match length.
+__device__ __noinline__ uint32_t long_lcp(Smem &sm, const uint8_t *s, uint32_t e, uint32_t d, uint32_t l, uint32_t cap,
+                                          uint32_t avail) {
+    const uint32_t j = e - d;
+    unsigned long long *set = sm.diag + (d & 15u) * 8;
+    uint32_t words = 0;
+    while (l < cap) {
+        if ((words++ & 15u) == 0) {  // is the rest of this diagonal already known?
+#pragma unroll
+            for (int way = 0; way < 8; way++) {
+                const unsigned long long ent = set[way];
+                const uint32_t st = (uint32_t)(ent >> 16) & 0xFFFFu, en = (uint32_t)ent & 0xFFFFu;
+                if ((uint32_t)(ent >> 32) == d && st <= e + l && e + l < en) l = en - e;
+            }
+            if (l >= cap) break;
+        }
+        const uint32_t x = lds32(s, j + l) ^ lds32(s, e + l);
+        if (x) {
+            l += (__ffs(x) - 1) >> 3;
+            break;
+        }
+        l += 4;
+    }
+    if (words >= 8 || l >= cap) {  // publish what was verified: equal on [e, e + l), clipped to staged bytes
+        uint32_t st = e, en = min(e + l, avail);
+        int victim = (int)((e >> 5) & 7u);
+#pragma unroll
+        for (int way = 0; way < 8; way++) {
+            const unsigned long long cur = set[way];
+            const uint32_t cst = (uint32_t)(cur >> 16) & 0xFFFFu, cen = (uint32_t)cur & 0xFFFFu;
+            if ((uint32_t)(cur >> 32) == d && cst <= en && st <= cen) {  // overlapping: keep the union
+                st = min(st, cst);
+                en = max(en, cen);
+                victim = way;
+            }
+        }
+        set[victim] = ((unsigned long long)d << 32) | ((unsigned long long)st << 16) | en;
+    }
+    return l;
 }
 
 // Candidates of the sorted slot r (entry e): the slots [lo, r) of its 3-gram group whose positions
@@ -236,6 +283,7 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
         }
     }
     for (int i = threadIdx.x; i < 16 * WARPS; i += THREADS) sm.ctr[i] = 0;
+    if (threadIdx.x < 128) sm.diag[threadIdx.x] = 0;  // d = 0 never matches a real distance
     __syncthreads();
     // ---- per tile slot: candidate range, work class.  Slots without candidates are final here.
     // Lanes of a warp later take slots of ONE class (similar candidate counts), which is what keeps
@@ -332,16 +380,21 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
                 const uint32_t j = arr[c];
                 if (j >= jlim) break;  // nearer candidates yield even less
                 if (sb[j] != tgt) continue;
-                const uint32_t cap = min(e - j, room);
+                const uint32_t d = e - j;
+                const uint32_t cap = min(d, room);
                 uint32_t l = 3;
-                while (l < cap) {
+                // short matches (the common case) stay in this tight loop; after 32 equal bytes the
+                // out-of-line routine takes over (diagonal cache)
+                while (l < cap && l < 35) {
                     const uint32_t x = lds32(s, j + l) ^ lds32(s, e + l);
                     if (x) {
                         l += (__ffs(x) - 1) >> 3;
-                        break;
+                        goto lcp_done;
                     }
                     l += 4;
                 }
+                if (l < cap) l = long_lcp(sm, s, e, d, l, cap, avail);
+            lcp_done:
                 l = min(l, cap);
                 if (l > best) {
                     best = l;

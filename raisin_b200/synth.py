@@ -148,6 +148,8 @@ def generate(kind: str, n: int, seed: int = 1) -> bytes:
         return random_bytes(n, seed)
     if kind == "mixed":
         return mixed(n, seed)
+    if kind == "repetitive":
+        return repetitive(n, seed, motif=3000)
     raise ValueError(kind)
 
 
