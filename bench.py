@@ -136,6 +136,78 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ batch workload
+
+
+def run_batch(args, rank, local_rank, world):
+    """BASELINE configs[3] shape: independent 256 KiB files (kind j mod 3, seed 1000 + j), layered
+    lzss,huffman, files partitioned round-robin over ranks; every rank runs `--files` of them through
+    rsn_batch_layers (host buffers in and out).  One step = compress all + decompress all."""
+    import torch
+    import torch.distributed as dist
+
+    import raisin_b200 as rsn
+    from raisin_b200 import parallel, synth
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = rsn._lib.lib()
+    rsn._lib.check(lib.rsn_init(local_rank))
+    mine = parallel.partition_files(args.files * world, world, rank)
+    files = [synth.batch_file(j) for j in mine]
+    total = sum(len(f) for f in files)
+    n = len(files)
+    keep = [rsn._lib._as_ptr(f) for f in files]
+    ins = (C.c_void_p * n)(*[k[0] for k in keep])
+    ns = (C.c_size_t * n)(*[k[1] for k in keep])
+
+    def step(check=False):
+        outs, out_ns, rcs = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        rsn._lib.check(lib.rsn_batch_layers(b"lzss,huffman", 1, n, ins, ns, outs, out_ns, rcs, args.workers, 0))
+        b_outs, b_ns = (C.c_void_p * n)(), (C.c_size_t * n)()
+        rsn._lib.check(lib.rsn_batch_layers(b"lzss,huffman", 0, n, outs, out_ns, b_outs, b_ns, rcs, args.workers, 0))
+        csum = sum(out_ns)
+        lossless = 0
+        if check:
+            lossless = sum(C.string_at(b_outs[i], b_ns[i]) == files[i] for i in range(n))
+        for i in range(n):
+            lib.rsn_free(outs[i])
+            lib.rsn_free(b_outs[i])
+        return csum, lossless
+
+    csum, lossless = step(check=True)
+    for _ in range(max(args.warmup, 3) - 1):
+        step()
+    lib.rsn_reset_kernel_launches()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        gbs = world * total / (ms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "lzss,huffman compress+decompress GB/s over a batch of independent files (host buffers)",
+            "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"batch of {n} x 256 KiB files per GPU (BASELINE configs[3] shape), lzss,huffman",
+                       "files_per_gpu": n, "bytes_per_gpu": total, "workers": args.workers},
+            "compressed_bytes_per_gpu": csum, "lossless_files": lossless, "of_files": n,
+            "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": total + csum, "d2h_bytes_per_step": total + csum},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ our arm
 
 
@@ -148,6 +220,10 @@ def main():
     ap.add_argument("--bytes", type=int, default=N_BYTES)
     ap.add_argument("--full-reference", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="stream", choices=["stream", "batch"],
+                    help="stream: BASELINE configs[1] (default, the headline); batch: configs[3] shape")
+    ap.add_argument("--files", type=int, default=512, help="batch workload: files per GPU (256 KiB each)")
+    ap.add_argument("--workers", type=int, default=16)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -157,6 +233,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "batch":
+        run_batch(args, rank, local_rank, world)
         return
 
     import numpy as np

@@ -88,6 +88,17 @@ int rsn_huff_decompress(const uint8_t *in, size_t n, int strict_limits, uint8_t 
 int rsn_compress_layers(const char *algorithms, const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
 int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
 
+/*
+ * Batches of independent files (BASELINE configs[3]): file i is compressed (or decompressed) with
+ * the layer list exactly as rsn_compress_layers would, on a pool of `workers` host threads (0 =
+ * default), each with its own CUDA stream, so many small per-file pipelines overlap on the GPU.
+ * out[i]/out_n[i] receive library-owned buffers (rsn_free each); rcs[i] (optional) the per-file
+ * code.  Returns RSN_OK or the first failing file's code.  With device != 0 the in/out pointers
+ * are device pointers (release with rsn_dev_free(p, NULL)).
+ */
+int rsn_batch_layers(const char *algorithms, int compress, size_t count, const uint8_t *const *in, const size_t *in_n,
+                     uint8_t **out, size_t *out_n, int *rcs, int workers, int device);
+
 /* ---- device-buffer API ------------------------------------------------------------------- */
 /*
  * Same operations with input and output resident in device memory of the context's device.

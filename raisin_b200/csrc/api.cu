@@ -170,6 +170,124 @@ int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, u
     return layers_host(algorithms, false, in, n, out, out_n);
 }
 
+// ---- batches of independent files
+
+}  // extern "C"
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+namespace rsn {
+namespace {
+// Persistent worker threads: each keeps its thread-local context (stream, arena) across batches.
+class WorkerPool {
+  public:
+    void run(int workers, const std::function<void()> &job) {
+        std::unique_lock<std::mutex> lk(mu_);
+        while ((int)threads_.size() < workers) threads_.emplace_back([this] { loop(); });
+        job_ = job;
+        pending_ = workers;
+        running_ = workers;
+        generation_++;
+        cv_.notify_all();
+        done_.wait(lk, [this] { return running_ == 0; });
+    }
+
+  private:
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return generation_ != seen && pending_ > 0; });
+                seen = generation_;
+                pending_--;
+                job = job_;
+            }
+            job();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--running_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> threads_;
+    std::function<void()> job_;
+    int pending_ = 0, running_ = 0;
+    uint64_t generation_ = 0;
+};
+WorkerPool &pool() {
+    static WorkerPool *p = new WorkerPool();  // threads live for the process
+    return *p;
+}
+}  // namespace
+}  // namespace rsn
+
+extern "C" {
+
+int rsn_batch_layers(const char *algorithms, int compress, size_t count, const uint8_t *const *in, const size_t *in_n,
+                     uint8_t **out, size_t *out_n, int *rcs, int workers, int device) {
+    if (!in || !in_n || !out || !out_n) return RSN_ERR_INVALID_ARG;
+    std::vector<Algo> algos;
+    RSN_TRY(parse_layers(algorithms, algos));
+    RSN_TRY(ensure_ctx());
+    const int dev = ctx().device;
+    if (workers <= 0) workers = 16;
+    if ((size_t)workers > count) workers = (int)(count ? count : 1);
+    std::atomic<size_t> next{0};
+    std::atomic<int> first_err{RSN_OK};
+    auto job = [&]() {
+        if (rsn_init(dev) != RSN_OK) {
+            int expect = RSN_OK;
+            first_err.compare_exchange_strong(expect, RSN_ERR_CUDA);
+            return;
+        }
+        cudaStream_t s = ctx().own_stream;
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= count) break;
+            int rc;
+            uint8_t *r = nullptr;
+            size_t rn = 0;
+            {
+                ArenaScope scope(s);
+                const uint8_t *d_in = in[i];
+                DevBuf d;
+                rc = RSN_OK;
+                if (!device) {
+                    rc = to_device(in[i], in_n[i], d, s);
+                    d_in = d.as<uint8_t>();
+                }
+                if (rc == RSN_OK) rc = layers_dev(algos, compress != 0, d_in, in_n[i], &r, &rn, s);
+                if (rc == RSN_OK) {
+                    if (device) {
+                        cudaStreamSynchronize(s);
+                        out[i] = r;
+                        out_n[i] = rn;
+                    } else {
+                        rc = to_host(r, rn, &out[i], &out_n[i], s);
+                    }
+                }
+            }
+            if (rc != RSN_OK) {
+                out[i] = nullptr;
+                out_n[i] = 0;
+                int expect = RSN_OK;
+                first_err.compare_exchange_strong(expect, rc);
+            }
+            if (rcs) rcs[i] = rc;
+        }
+    };
+    pool().run(workers, job);
+    return first_err.load();
+}
+
 // ---- device-buffer API
 
 // stream == NULL: run on the context's own stream and synchronise before returning

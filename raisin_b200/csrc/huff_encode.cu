@@ -253,13 +253,9 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     huff_header(leaves, hdr);
     std::vector<CodeEntry> h_codes(codes.size());
     uint64_t total_bits = 0;
-    {
-        std::vector<uint64_t> fr(kRuneSpace, 0);
-        for (const HuffLeaf &l : leaves) fr[l.rune] = (uint64_t)l.freq;
-        for (size_t i = 0; i < codes.size(); i++) {
-            h_codes[i] = CodeEntry{(uint32_t)codes[i].rune, codes[i].len, codes[i].code};
-            total_bits += (uint64_t)codes[i].len * fr[codes[i].rune];
-        }
+    for (size_t i = 0; i < codes.size(); i++) {
+        h_codes[i] = CodeEntry{(uint32_t)codes[i].rune, codes[i].len, codes[i].code};
+        total_bits += (uint64_t)codes[i].len * (uint64_t)codes[i].freq;
     }
     const uint32_t pad = (uint32_t)((8 - total_bits % 8) % 8);  // huffman.go:245-249
     const size_t payload = (size_t)((total_bits + pad) / 8);

@@ -99,7 +99,7 @@ bool huff_codes(const HuffTree &t, std::vector<HuffCode> &codes) {
         const HuffNode &nd = t.nodes[it.node];
         if (nd.left < 0) {
             if (it.depth > 64) ok = false;
-            codes.push_back(HuffCode{nd.right, (uint8_t)std::min<uint32_t>(it.depth, 255), it.code});
+            codes.push_back(HuffCode{nd.right, (uint8_t)std::min<uint32_t>(it.depth, 255), it.code, t.freq[it.node]});
             continue;
         }
         stack.push_back({nd.right, it.depth + 1, (it.code << 1) | 1});  // right appends '1'

@@ -32,6 +32,7 @@ struct HuffCode {
     int32_t rune;
     uint8_t len;
     uint64_t code;  // MSB-first in the low `len` bits
+    int64_t freq;   // the leaf's frequency
 };
 // printCodes (huffman.go:110-127).  Returns false if a code is longer than 64 bits.
 bool huff_codes(const HuffTree &t, std::vector<HuffCode> &codes);

@@ -76,6 +76,30 @@ def decompress_fused(content, algorithms) -> bytes:
         lambda p, n, o, on: _lib.lib().rsn_decompress_layers(",".join(algorithms).encode(), p, n, o, on), content)
 
 
+def batch(files, algorithms, compress_: bool = True, workers: int = 0):
+    """Independent files through the layer list on a pool of host threads/streams (one C-ABI call).
+    Returns a list with one bytes object per file; a failed file (the reference would panic) is None."""
+    import ctypes as C
+
+    L = _lib.lib()
+    n = len(files)
+    keep = [_lib._as_ptr(f) for f in files]
+    ins = (C.c_void_p * n)(*[k[0] for k in keep])
+    ns = (C.c_size_t * n)(*[k[1] for k in keep])
+    outs = (C.c_void_p * n)()
+    out_ns = (C.c_size_t * n)()
+    rcs = (C.c_int * n)()
+    L.rsn_batch_layers(",".join(algorithms).encode(), 1 if compress_ else 0, n, ins, ns, outs, out_ns, rcs, workers, 0)
+    res = []
+    for i in range(n):
+        if rcs[i] != 0:
+            res.append(None)
+        else:
+            res.append(C.string_at(outs[i], out_ns[i]))
+            L.rsn_free(outs[i])
+    return res
+
+
 def CompressFile(algorithms, path: str, output: str | None = None) -> str:
     """engine.go:157-166: whole file in, `<path>.rsn` out (no framing, no magic)."""
     with open(path, "rb") as fh:

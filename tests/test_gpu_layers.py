@@ -68,3 +68,24 @@ def test_mixed_corpus_config3_shape(rsn, oracle):
     got = rsn.engine.compress_fused(data, ALGOS)
     assert got == want
     assert rsn.engine.decompress_fused(got, ALGOS) == oracle.lzss_decompress(oracle.huff_decompress(want))
+
+
+def test_batch_of_files(rsn, oracle):
+    """BASELINE configs[3] shape (files j = kind j mod 3, seed 1000 + j) at a size the oracle checks quickly."""
+    files = [synth.batch_file(j, 48 * 1024) for j in range(24)] + [b"", b"a", b"<\\" * 50]
+    got = rsn.engine.batch(files, ALGOS, True, workers=6)
+    for f, g in zip(files, got):
+        if not f:
+            assert g is None          # empty input: huffman layer panics in the reference
+        else:
+            assert g == oracle.huff_compress(oracle.lzss_compress_async(f, 4096))
+    back = rsn.engine.batch([g for g in got if g is not None], ALGOS, False, workers=6)
+    k = 0
+    for f, g in zip(files, got):
+        if g is None:
+            continue
+        assert back[k] == oracle.lzss_decompress(oracle.huff_decompress(g))
+        k += 1
+    # lzss alone is lossless on every file
+    lz = rsn.engine.batch(files, ["lzss"], True)
+    assert rsn.engine.batch(lz, ["lzss"], False) == files
