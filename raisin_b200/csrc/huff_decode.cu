@@ -18,45 +18,70 @@ namespace rsn {
 
 constexpr uint32_t kSubBits = 256;  // bits per subsequence (one thread)
 
+constexpr int kLutBits = 12;
+
 struct DecParams {
-    const uint8_t *bits;   // payload bytes after the pad byte
-    uint64_t diff;         // pad bits to skip
-    uint64_t max;          // number of code bits
+    const uint32_t *words;  // payload as 4-byte words from an aligned base
+    uint64_t nwords;        // words that may be read (the rest reads as 0)
+    uint64_t bit0;          // bit offset of code bit 0 from that base (alignment slack + pad bits)
+    uint64_t max;           // number of code bits
     const HuffNode *nodes;
+    const uint32_t *lut;    // 2^kLutBits entries: leaf -> 1<<31 | len<<21 | rune ; else node index after kLutBits bits
     int32_t root;
 };
 
-__device__ __forceinline__ uint32_t get_bit(const DecParams &p, uint64_t i) {
-    const uint64_t b = p.diff + i;
-    return (__ldg(p.bits + (b >> 3)) >> (7 - (uint32_t)(b & 7))) & 1u;
+// the 32 stream bits starting at code bit i, MSB first (bytes are big-endian bit order in memory)
+__device__ __forceinline__ uint32_t peek32(const DecParams &p, uint64_t i) {
+    const uint64_t b = p.bit0 + i;
+    const uint64_t w = b >> 5;
+    const uint32_t hi = w < p.nwords ? __byte_perm(__ldg(p.words + w), 0, 0x0123) : 0u;
+    const uint32_t lo = w + 1 < p.nwords ? __byte_perm(__ldg(p.words + w + 1), 0, 0x0123) : 0u;
+    return __funnelshift_l(lo, hi, (uint32_t)(b & 31));
 }
 
 // Decode codes that START in [pos, limit).  Returns the position after the last complete code
 // (>= limit unless the bits ran out).  `truncated` is set if the bits end inside a code.
-// If OUT is non-null the UTF-8 bytes are written there.
+// With WRITE the UTF-8 bytes are stored at out.
 template <bool WRITE>
 __device__ __forceinline__ uint64_t decode_span(const DecParams &p, uint64_t pos, uint64_t limit, uint64_t &bytes,
                                                 bool &truncated, uint8_t *out) {
     bytes = 0;
     truncated = false;
     while (pos < limit) {
-        int32_t node = p.root;
-        HuffNode nd = p.nodes[node];
-        uint64_t q = pos;
-        while (nd.left >= 0) {
-            if (q >= p.max) {
+        const uint32_t win = peek32(p, pos);
+        const uint32_t ent = __ldg(p.lut + (win >> (32 - kLutBits)));
+        int32_t rune;
+        uint64_t q;
+        if (ent >> 31) {
+            const uint32_t len = (ent >> 21) & 0x3FFu;
+            q = pos + len;
+            if (q > p.max) {  // the code would need bits past the end (huffman.go:145)
                 truncated = true;
-                return q;
+                return p.max;
             }
-            node = get_bit(p, q) ? nd.right : nd.left;
-            nd = p.nodes[node];
-            q++;
+            rune = (int32_t)(ent & 0x1FFFFFu);
+        } else {  // longer than the table: finish on the tree
+            int32_t node = (int32_t)ent;
+            q = pos + kLutBits;
+            if (q > p.max) {
+                truncated = true;
+                return p.max;
+            }
+            HuffNode nd = p.nodes[node];
+            while (nd.left >= 0) {
+                if (q >= p.max) {
+                    truncated = true;
+                    return q;
+                }
+                const uint32_t bit = peek32(p, q) >> 31;
+                node = bit ? nd.right : nd.left;
+                nd = p.nodes[node];
+                q++;
+            }
+            rune = nd.right;
         }
-        if (WRITE) {
-            bytes += (uint64_t)utf8_encode(nd.right, out + bytes);
-        } else {
-            bytes += (uint64_t)utf8_width(nd.right);
-        }
+        if (WRITE) bytes += (uint64_t)utf8_encode(rune, out + bytes);
+        else bytes += (uint64_t)utf8_width(rune);
         pos = q;
     }
     return pos;
@@ -133,7 +158,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
         sp = find_sep(h, n);
     } else {
         // device-resident input: pull a prefix, then everything if the header is longer
-        size_t take = n < ((size_t)1 << 20) ? n : ((size_t)1 << 20);
+        size_t take = n < ((size_t)64 << 10) ? n : ((size_t)64 << 10);
         for (;;) {
             h_copy.resize(take);
             RSN_CUDA(cudaMemcpyAsync(h_copy.data(), d_in, take, cudaMemcpyDeviceToHost, s));
@@ -192,11 +217,35 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
     RSN_TRY(nodes.alloc(tree.nodes.size() * sizeof(HuffNode), s));
     RSN_CUDA(cudaMemcpyAsync(nodes.p, tree.nodes.data(), tree.nodes.size() * sizeof(HuffNode), cudaMemcpyHostToDevice, s));
 
+    // lookup table over the first kLutBits bits of a code
+    std::vector<uint32_t> h_lut((size_t)1 << kLutBits);
+    for (uint32_t idx = 0; idx < h_lut.size(); idx++) {
+        int32_t node = tree.root;
+        uint32_t len = 0;
+        while (tree.nodes[node].left >= 0 && len < (uint32_t)kLutBits) {
+            const uint32_t bit = (idx >> (kLutBits - 1 - len)) & 1u;
+            node = bit ? tree.nodes[node].right : tree.nodes[node].left;
+            len++;
+        }
+        if (tree.nodes[node].left < 0) h_lut[idx] = (1u << 31) | (len << 21) | ((uint32_t)tree.nodes[node].right & 0x1FFFFFu);
+        else h_lut[idx] = (uint32_t)node;
+    }
+    DevBuf lut;
+    RSN_TRY(lut.alloc(h_lut.size() * 4, s));
+    RSN_CUDA(cudaMemcpyAsync(lut.p, h_lut.data(), h_lut.size() * 4, cudaMemcpyHostToDevice, s));
+
     DecParams p;
-    p.bits = d_in + pay_off + 1;
-    p.diff = diff;
+    {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(d_in + pay_off + 1);
+        p.words = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        p.bit0 = (uint64_t)(addr & 3) * 8 + diff;
+        p.nwords = ((addr & 3) + (pn - 1)) / 4;  // whole words inside the buffer; a ragged tail word is
+        // still inside the allocation when the base is 4-byte aligned, which device buffers are
+        if (((addr & 3) + (pn - 1)) % 4) p.nwords += 1;
+    }
     p.max = max;
     p.nodes = nodes.as<HuffNode>();
+    p.lut = lut.as<uint32_t>();
     p.root = tree.root;
 
     const size_t subs = (size_t)div_up(max, kSubBits);

@@ -89,3 +89,29 @@ def test_batch_of_files(rsn, oracle):
     # lzss alone is lossless on every file
     lz = rsn.engine.batch(files, ["lzss"], True)
     assert rsn.engine.batch(lz, ["lzss"], False) == files
+
+
+def test_cli_rsn_interchange(rsn, oracle, tmp_path):
+    """The C++ host mirror + CLI (raisin_b200/host): `-algorithm=lzss,huffman` writes the same .rsn
+    bytes the oracle predicts for stock raisin, decompresses it back, and -benchmark reports Lossless."""
+    import subprocess
+
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "raisin_b200", "raisin_b200_cli")
+    data = synth.text(150000, 9)
+    p = tmp_path / "alice.txt"
+    p.write_bytes(data)
+    subprocess.check_call([cli, "-algorithm=lzss,huffman", str(p)])
+    blob = (tmp_path / "alice.txt.rsn").read_bytes()
+    assert blob == oracle.huff_compress(oracle.lzss_compress_async(data, 4096, threads=8))
+    subprocess.check_call([cli, "-decompress", "-algorithm=lzss,huffman", f"-out={tmp_path / 'back.txt'}",
+                           str(tmp_path / "alice.txt.rsn")])
+    assert (tmp_path / "back.txt").read_bytes() == data
+    out = subprocess.check_output([cli, "-benchmark", "-algorithm=lzss,huffman,[lzss,huffman]", str(p)], text=True)
+    rows = [l.split() for l in out.splitlines() if l and not l.startswith(("ENGINE", "File"))]
+    assert [r[0] for r in rows] == ["lzss", "huffman", "lzss,huffman"]
+    assert all(r[-1] == "true" for r in rows)
+    # empty file: the huffman layer panics in the reference -> DNF row, exit code still 0
+    e = tmp_path / "empty"
+    e.write_bytes(b"")
+    out = subprocess.check_output([cli, "-benchmark", "-algorithm=huffman", str(e)], text=True)
+    assert "DNF" in out
