@@ -275,10 +275,14 @@ constexpr int kHops = 64;
 // shortened in place (dist[o] := distance to the furthest ancestor reached) and finished by a
 // later round; both the old and the new distance name a true ancestor, so concurrent readers
 // are safe.  Literal bytes (dist == 0) are never written here.
+// `work` == nullptr: first round, one thread per output byte; unfinished bytes are appended to
+// `work_out`.  Later rounds walk the previous round's list only.
 __global__ void __launch_bounds__(256) k_resolve(uint8_t *__restrict__ sb, uint32_t *__restrict__ dist, size_t n,
-                                                 uint32_t *__restrict__ unfinished) {
-    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= n) return;
+                                                 const uint32_t *__restrict__ work, uint32_t *__restrict__ work_out,
+                                                 uint32_t *__restrict__ work_count) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t o = work ? work[t] : t;
     uint32_t d = dist[o];
     if (d == 0) return;
     size_t p = o - d;
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(256) k_resolve(uint8_t *__restrict__ sb, uint3
     if (dp == 0) {
         sb[o] = sb[p];
     } else {
-        *unfinished = 1;
+        work_out[atomicAdd(work_count, 1u)] = (uint32_t)o;  // rare: chains deeper than kHops
     }
     if (hops) dist[o] = (uint32_t)(o - p);
 }
@@ -482,16 +486,23 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
                sb.as<uint8_t>(), dist.as<uint32_t>(), err.as<uint32_t>());
     tr.mark("scatter");
     if (sbn) {
-        uint32_t *unfinished = err.as<uint32_t>() + 1;
-        for (int round = 0; round < 64; round++) {
-            RSN_CUDA(cudaMemsetAsync(unfinished, 0, 4, s));
-            RSN_LAUNCH(k_resolve, (unsigned)div_up(sbn, 256), 256, 0, s, sb.as<uint8_t>(), dist.as<uint32_t>(),
-                       (size_t)sbn, unfinished);
+        // round 0 visits every byte; bytes whose chain is deeper than kHops go to a work list (their
+        // distance already shortened), and later rounds only walk that list
+        DevBuf wl[2];
+        RSN_TRY(wl[0].alloc(sbn * 4 + 16, s));
+        RSN_TRY(wl[1].alloc(sbn * 4 + 16, s));
+        uint32_t *count = err.as<uint32_t>() + 1;
+        size_t todo = (size_t)sbn;
+        for (int round = 0; todo; round++) {
+            RSN_CUDA(cudaMemsetAsync(count, 0, 4, s));
+            RSN_LAUNCH(k_resolve, (unsigned)div_up(todo, 256), 256, 0, s, sb.as<uint8_t>(), dist.as<uint32_t>(), todo,
+                       round ? wl[(round + 1) & 1].as<uint32_t>() : (const uint32_t *)nullptr, wl[round & 1].as<uint32_t>(),
+                       count);
             RSN_CUDA(cudaMemcpyAsync(c.h_scalars, err.p, 8, cudaMemcpyDeviceToHost, s));
             RSN_CUDA(cudaStreamSynchronize(s));
-            const uint32_t e = (uint32_t)c.h_scalars[0], u = (uint32_t)(c.h_scalars[0] >> 32);
+            const uint32_t e = (uint32_t)c.h_scalars[0];
             if (e & ERR_BAD_REF) return RSN_ERR_BAD_REFERENCE;
-            if (!u) break;
+            todo = (size_t)(uint32_t)(c.h_scalars[0] >> 32);
         }
     }
     tr.mark("resolve");
