@@ -94,12 +94,98 @@ __global__ void __launch_bounds__(1024) k_tok_spine(const uint8_t *__restrict__ 
     }
 }
 
-// st[i] = state in front of byte i
-__global__ void __launch_bounds__(kTileThreads) k_tok_states(const uint8_t *__restrict__ in, size_t n,
-                                                             const uint8_t *__restrict__ tile_state,
-                                                             uint8_t *__restrict__ st) {
+// ============================================================================= K5b/K5c tokens
+
+// strconv.Atoi (Go 1.15) fed one byte at a time, error dropped as lzss.go:338,346 do: a syntax
+// error yields 0, a range error the clamped int64 extreme; whichever comes first wins because
+// Go's scan stops at the first offending byte.
+struct GoAtoi {
+    uint64_t un = 0;
+    bool first = true, neg = false, any = false, bad = false, range = false;
+    __device__ __forceinline__ void feed(uint8_t c) {
+        if (first) {
+            first = false;
+            if (c == '+' || c == '-') {
+                neg = c == '-';
+                return;
+            }
+        }
+        if (bad || range) return;
+        if (c < '0' || c > '9') {
+            bad = true;
+            return;
+        }
+        any = true;
+        const uint64_t maxv = ~0ull, cutoff = maxv / 10 + 1;
+        if (un >= cutoff) {
+            range = true;
+            return;
+        }
+        un *= 10;
+        const uint64_t n1 = un + (uint64_t)(c - '0');
+        if (n1 < un) {
+            range = true;
+            return;
+        }
+        un = n1;
+    }
+    __device__ __forceinline__ int64_t value() const {
+        if (bad || !any) return 0;
+        const uint64_t icut = 1ull << 63;
+        const uint64_t u = range ? ~0ull : un;
+        if (!neg && u >= icut) return INT64_MAX;
+        if (neg && u > icut) return INT64_MIN;
+        return neg ? -(int64_t)u : (int64_t)u;
+    }
+};
+
+// The token that opens at in[i] ('<' seen in state Open): scan forward to the first ',' then the
+// first '>' exactly as the state machine of lzss.go:333-360 does.  Returns false if the input ends
+// first (the reference silently drops an unterminated token).
+__device__ __forceinline__ bool parse_token_fwd(const uint8_t *__restrict__ in, size_t n, size_t i, int64_t &ptr,
+                                                int64_t &cnt) {
+    GoAtoi a, b;
+    size_t j = i + 1;
+    for (;; j++) {
+        if (j >= n) return false;
+        const uint8_t c = __ldg(in + j);
+        if (c == 0x2C) break;
+        a.feed(c);
+    }
+    for (j++;; j++) {
+        if (j >= n) return false;
+        const uint8_t c = __ldg(in + j);
+        if (c == 0x3E) break;
+        b.feed(c);
+    }
+    ptr = a.value();
+    cnt = b.value();
+    return true;
+}
+
+enum : uint32_t { ERR_BAD_REF = 1u, FLAG_NEEDS_UNESCAPE = 2u };
+constexpr int kMaxTok = kTile / 3 + 2;  // "<,>" is the shortest token
+
+// One tile of the compressed stream.  Threads first classify their 16 bytes (state machine from
+// the tile's incoming state), the token openers of the whole tile are compacted into a list, and
+// the list is parsed with one token per thread (so token parsing runs on full warps instead of
+// one lane at a time).  WRITE == false: output bytes of the tile.  WRITE == true: literals to
+// sb, pointer distances of referenced bytes to dist (zero-filled beforehand).
+template <bool WRITE>
+__global__ void __launch_bounds__(kTileThreads) k_tok_tile(const uint8_t *__restrict__ in, size_t n,
+                                                           const uint8_t *__restrict__ tile_state,
+                                                           const uint64_t *__restrict__ tile_off,
+                                                           uint64_t *__restrict__ tile_out, uint8_t *__restrict__ sb,
+                                                           uint32_t *__restrict__ dist, uint32_t *__restrict__ err) {
     __shared__ uint8_t buf[kTileThreads];
-    const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
+    __shared__ uint64_t sm64[33];
+    __shared__ uint32_t sm32[33];
+    __shared__ uint16_t list[kMaxTok];
+    __shared__ uint64_t tcnt[kMaxTok];
+    __shared__ uint64_t tptr[WRITE ? kMaxTok : 1];
+    __shared__ uint64_t toff[WRITE ? kMaxTok : 1];
+    const size_t tile_base = (size_t)blockIdx.x * kTile;
+    const size_t base = tile_base + (size_t)threadIdx.x * kItems;
     uint8_t v[16];
     int valid = 0;
     uint8_t m = kMapId;
@@ -110,160 +196,89 @@ __global__ void __launch_bounds__(kTileThreads) k_tok_states(const uint8_t *__re
     }
     block_inclusive_scan_generic<uint8_t>(m, buf, MapCompose());
     const uint8_t exc = threadIdx.x ? buf[threadIdx.x - 1] : kMapId;
-    uint8_t s = map_apply(exc, tile_state[blockIdx.x]);
-    if (valid == 16 && ((reinterpret_cast<uintptr_t>(st + base) & 15) == 0)) {
-        uint32_t w[4] = {0, 0, 0, 0};
+    uint8_t st = map_apply(exc, tile_state[blockIdx.x]);
+    uint32_t lit_mask = 0, open_mask = 0, flags = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < valid) {
+            const uint8_t b = v[k];
+            if (st == ST_OPEN) {
+                if (b == 0x3C) open_mask |= 1u << k;
+                else {
+                    lit_mask |= 1u << k;
+                    if (b == 0x5C || b == 0xFF) flags |= FLAG_NEEDS_UNESCAPE;
+                }
+            }
+            st = map_apply(tok_map_of(b), st);
+        }
+    }
+    // compact the token openers of the tile
+    const uint32_t ntok = __popc(open_mask);
+    uint32_t T;
+    const uint32_t tbase = block_exclusive_sum<uint32_t>(ntok, sm32, T);
+    {
+        uint32_t j = tbase;
+        for (uint32_t mk = open_mask; mk; mk &= mk - 1) list[j++] = (uint16_t)(threadIdx.x * kItems + (__ffs(mk) - 1));
+    }
+    __syncthreads();
+    // one token per thread
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+        int64_t ptr = 0, cnt = 0;
+        if (parse_token_fwd(in, n, tile_base + list[t], ptr, cnt)) {
+            if (cnt < 0 || ptr < cnt) {  // a = len - ptr: need 0 <= a <= a + cnt <= len (lzss.go:349-350)
+                flags |= ERR_BAD_REF;
+                cnt = 0;
+            }
+        } else {
+            cnt = 0;  // unterminated at end of input: dropped
+        }
+        tcnt[t] = (uint64_t)cnt;
+        if (WRITE) tptr[t] = (uint64_t)ptr;
+    }
+    __syncthreads();
+    uint64_t c = __popc(lit_mask);
+    for (uint32_t j = 0; j < ntok; j++) c += tcnt[tbase + j];
+    uint64_t total;
+    const uint64_t pre = block_exclusive_sum<uint64_t>(c, sm64, total);
+    if (!WRITE) {
+        if (threadIdx.x == 0) tile_out[blockIdx.x] = total;
+        if (flags) atomicOr(err, flags);
+        return;
+    }
+    // literals in place, token output offsets for the fill phase
+    uint64_t o = tile_off[blockIdx.x] + pre;
+    {
+        uint32_t j = tbase;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            w[k >> 2] |= (uint32_t)s << ((k & 3) * 8);
-            s = map_apply(tok_map_of(v[k]), s);
-        }
-        *reinterpret_cast<uint4 *>(st + base) = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-        for (int k = 0; k < valid; k++) {
-            st[base + k] = s;
-            s = map_apply(tok_map_of(v[k]), s);
-        }
-    }
-}
-
-// ============================================================================= K5b token parse
-
-// strconv.Atoi (Go 1.15) with the error dropped, over in[a, b): syntax error => 0, range error
-// => clamped int64 extreme (lzss.go:338, 346 discard the error).
-__device__ int64_t go_atoi_dev(const uint8_t *__restrict__ in, size_t a, size_t b) {
-    if (a >= b) return 0;
-    bool neg = false;
-    uint8_t c0 = in[a];
-    if (c0 == '+' || c0 == '-') {
-        neg = c0 == '-';
-        a++;
-        if (a >= b) return 0;
-    }
-    const uint64_t maxv = ~0ull, cutoff = maxv / 10 + 1;
-    uint64_t un = 0;
-    for (size_t i = a; i < b; i++) {
-        const uint8_t c = in[i];
-        if (c < '0' || c > '9') return 0;
-        if (un >= cutoff) {
-            un = maxv;
-            break;
-        }
-        un *= 10;
-        const uint64_t n1 = un + (uint64_t)(c - '0');
-        if (n1 < un) {
-            un = maxv;
-            break;
-        }
-        un = n1;
-    }
-    const uint64_t icut = 1ull << 63;
-    if (!neg && un >= icut) return INT64_MAX;
-    if (neg && un > icut) return INT64_MIN;
-    const int64_t v = (int64_t)un;
-    return neg ? -v : v;
-}
-
-// For a closing '>' at i (state Close): locate the token's separator and opening by walking the
-// state array backwards, and evaluate pointer and count as the reference does.
-__device__ __forceinline__ void parse_token(const uint8_t *__restrict__ in, const uint8_t *__restrict__ st, size_t i,
-                                            int64_t &ptr, int64_t &cnt) {
-    size_t j = i;  // bytes (j, i) carry state Close; j is the ',' (state Sep in front of it)
-    while (st[j - 1] == ST_CLOSE) j--;
-    j--;
-    size_t k = j;  // bytes (k, j) carry state Sep; k is the '<'
-    while (st[k - 1] == ST_SEP) k--;
-    k--;
-    ptr = go_atoi_dev(in, k + 1, j);
-    cnt = go_atoi_dev(in, j + 1, i);
-}
-
-enum : uint32_t { ERR_BAD_REF = 1u, FLAG_NEEDS_UNESCAPE = 2u };
-
-// out-size contribution of byte i (literal: 1, closing '>': cnt, else 0)
-__device__ __forceinline__ uint64_t tok_contrib(const uint8_t *__restrict__ in, const uint8_t *__restrict__ st,
-                                                size_t i, uint8_t b, uint8_t s, uint32_t *err) {
-    if (s == ST_OPEN) {
-        if (b == 0x3C) return 0;
-        if (err && (b == 0x5C || b == 0xFF)) atomicOr(err, FLAG_NEEDS_UNESCAPE);  // rare bytes
-        return 1;
-    }
-    if (s == ST_CLOSE && b == 0x3E) {
-        int64_t ptr, cnt;
-        parse_token(in, st, i, ptr, cnt);
-        if (cnt < 0 || ptr < cnt) {  // a = len-ptr, need 0 <= a <= a+cnt <= len
-            if (err) atomicOr(err, ERR_BAD_REF);
-            return 0;
-        }
-        return (uint64_t)cnt;
-    }
-    return 0;
-}
-
-__global__ void __launch_bounds__(kTileThreads) k_tok_sizes(const uint8_t *__restrict__ in,
-                                                            const uint8_t *__restrict__ st, size_t n,
-                                                            uint64_t *__restrict__ tile_out,
-                                                            uint32_t *__restrict__ err) {
-    __shared__ uint64_t sm[33];
-    const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
-    uint64_t c = 0;
-    if (base < n) {
-        uint8_t v[16], sv[16];
-        load16(in, base, n, 0, v);
-        load16(st, base, n, 0, sv);
-        const int valid = (int)min((size_t)16, n - base);
-        for (int k = 0; k < valid; k++) c += tok_contrib(in, st, base + k, v[k], sv[k], err);
-    }
-    uint64_t total;
-    block_exclusive_sum<uint64_t>(c, sm, total);
-    if (threadIdx.x == 0) tile_out[blockIdx.x] = total;
-}
-
-// ============================================================================= K5c scatter
-
-// sb[o] = literal bytes; dist[o] = 0 for literals, pointer distance for referenced bytes.
-__global__ void __launch_bounds__(kTileThreads) k_tok_scatter(const uint8_t *__restrict__ in,
-                                                              const uint8_t *__restrict__ st, size_t n,
-                                                              const uint64_t *__restrict__ tile_off,
-                                                              uint8_t *__restrict__ sb, uint32_t *__restrict__ dist,
-                                                              uint32_t *__restrict__ err) {
-    __shared__ uint64_t sm[33];
-    const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
-    uint8_t v[16], sv[16];
-    int valid = 0;
-    uint64_t c = 0;
-    if (base < n) {
-        load16(in, base, n, 0, v);
-        load16(st, base, n, 0, sv);
-        valid = (int)min((size_t)16, n - base);
-        for (int k = 0; k < valid; k++) c += tok_contrib(in, st, base + k, v[k], sv[k], nullptr);
-    }
-    uint64_t total;
-    uint64_t o = tile_off[blockIdx.x] + block_exclusive_sum<uint64_t>(c, sm, total);
-    for (int k = 0; k < valid; k++) {
-        const uint8_t b = v[k], s = sv[k];
-        if (s == ST_OPEN) {
-            if (b != 0x3C) {
-                sb[o] = b;
-                dist[o] = 0;
-                o++;
+            if (lit_mask & (1u << k)) sb[o++] = v[k];
+            else if (open_mask & (1u << k)) {
+                toff[j] = o;
+                o += tcnt[j];
+                j++;
             }
-        } else if (s == ST_CLOSE && b == 0x3E) {
-            int64_t ptr, cnt;
-            parse_token(in, st, base + k, ptr, cnt);
-            if (cnt < 0 || ptr < cnt) continue;  // already flagged by k_tok_sizes
-            if ((uint64_t)ptr > o) {             // absolutePointer < 0 (lzss.go:349)
-                atomicOr(err, ERR_BAD_REF);
-                // keep offsets consistent: mark the bytes as literals of value 0
-                for (int64_t q = 0; q < cnt; q++) {
-                    sb[o + q] = 0;
-                    dist[o + q] = 0;
-                }
-            } else {
-                for (int64_t q = 0; q < cnt; q++) dist[o + q] = (uint32_t)ptr;
-            }
-            o += (uint64_t)cnt;
         }
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+        const uint64_t cnt = tcnt[t], ptr = tptr[t], off = toff[t];
+        if (ptr > off) {  // absolutePointer < 0 (lzss.go:349): a panic even for an empty slice
+            atomicOr(err, ERR_BAD_REF);
+            continue;
+        }
+        if (cnt == 0) continue;
+        if (cnt <= 256) {
+            for (uint64_t q = 0; q < cnt; q++) dist[off + q] = (uint32_t)ptr;
+            tcnt[t] = 0;  // done; longer ones are filled by the whole CTA below
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = 0; t < T; t++) {
+        const uint64_t cnt = tcnt[t];
+        if (cnt <= 256) continue;
+        const uint64_t ptr = tptr[t], off = toff[t];
+        if (ptr > off) continue;
+        for (uint64_t q = threadIdx.x; q < cnt; q += blockDim.x) dist[off + q] = (uint32_t)ptr;
     }
 }
 
@@ -454,38 +469,37 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
     if (n == 0) return lzss_unescape(d_in, 0, d_out, out_n, s);
     const size_t tiles = div_up(n, kTile);
     Trace tr("lzd", s);
-    DevBuf tmap, tstate, st, tout, toff, err;
+    DevBuf tmap, tstate, tout, toff, err;
     RSN_TRY(tmap.alloc(tiles, s));
     RSN_TRY(tstate.alloc(tiles, s));
-    RSN_TRY(st.alloc(n + 16, s));
     RSN_TRY(tout.alloc(tiles * 8, s));
     RSN_TRY(toff.alloc((tiles + 1) * 8, s));
     RSN_TRY(err.alloc(16, s));
     RSN_CUDA(cudaMemsetAsync(err.p, 0, 16, s));
-    tr.mark("alloc");
     RSN_LAUNCH(k_tok_reduce, (unsigned)tiles, kTileThreads, 0, s, d_in, n, tmap.as<uint8_t>());
     RSN_LAUNCH(k_tok_spine, 1, 1024, 0, s, tmap.as<uint8_t>(), tiles, tstate.as<uint8_t>());
-    RSN_LAUNCH(k_tok_states, (unsigned)tiles, kTileThreads, 0, s, d_in, n, tstate.as<uint8_t>(), st.as<uint8_t>());
-    RSN_LAUNCH(k_tok_sizes, (unsigned)tiles, kTileThreads, 0, s, d_in, st.as<uint8_t>(), n, tout.as<uint64_t>(),
+    RSN_LAUNCH(k_tok_tile<false>, (unsigned)tiles, kTileThreads, 0, s, d_in, n, tstate.as<uint8_t>(),
+               (const uint64_t *)nullptr, tout.as<uint64_t>(), (uint8_t *)nullptr, (uint32_t *)nullptr,
                err.as<uint32_t>());
     RSN_TRY(spine_scan_u64(tout.as<uint64_t>(), toff.as<uint64_t>(), toff.as<uint64_t>() + tiles, tiles, s));
-    uint64_t sbn = 0;
-    RSN_TRY(read_u64(toff.as<uint64_t>() + tiles, &sbn, s));
     Ctx &c = ctx();
-    RSN_CUDA(cudaMemcpyAsync(c.h_scalars, err.p, 8, cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaMemcpyAsync(c.h_scalars, toff.as<uint64_t>() + tiles, 8, cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaMemcpyAsync(c.h_scalars + 1, err.p, 8, cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaStreamSynchronize(s));
-    if ((uint32_t)c.h_scalars[0] & ERR_BAD_REF) return RSN_ERR_BAD_REFERENCE;
+    const uint64_t sbn = c.h_scalars[0];
+    const uint32_t flags = (uint32_t)c.h_scalars[1];
+    if (flags & ERR_BAD_REF) return RSN_ERR_BAD_REFERENCE;
     if (sbn >= (1ull << 32)) return RSN_ERR_UNSUPPORTED;  // u32 source distances (documented limit)
-    tr.mark("states+sizes");
-    const bool needs_unescape = ((uint32_t)c.h_scalars[0] & FLAG_NEEDS_UNESCAPE) != 0;
+    tr.mark("plan");
+    const bool needs_unescape = (flags & FLAG_NEEDS_UNESCAPE) != 0;
     DevBuf sb, dist;  // sb becomes the result itself when no literal needs un-escaping
     RSN_TRY(sb.alloc_out(sbn + 16, s));
-    RSN_TRY(dist.alloc(sbn * 4 + 16, s));
-    tr.mark("alloc sb/dist");
-    RSN_LAUNCH(k_tok_scatter, (unsigned)tiles, kTileThreads, 0, s, d_in, st.as<uint8_t>(), n, toff.as<uint64_t>(),
-               sb.as<uint8_t>(), dist.as<uint32_t>(), err.as<uint32_t>());
-    tr.mark("scatter");
     if (sbn) {
+        RSN_TRY(dist.alloc(sbn * 4 + 16, s));
+        RSN_CUDA(cudaMemsetAsync(dist.p, 0, sbn * 4 + 16, s));
+        RSN_LAUNCH(k_tok_tile<true>, (unsigned)tiles, kTileThreads, 0, s, d_in, n, tstate.as<uint8_t>(),
+                   toff.as<uint64_t>(), (uint64_t *)nullptr, sb.as<uint8_t>(), dist.as<uint32_t>(), err.as<uint32_t>());
+        tr.mark("scatter");
         // round 0 visits every byte; bytes whose chain is deeper than kHops go to a work list (their
         // distance already shortened), and later rounds only walk that list
         DevBuf wl[2];
@@ -504,8 +518,8 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
             if (e & ERR_BAD_REF) return RSN_ERR_BAD_REFERENCE;
             todo = (size_t)(uint32_t)(c.h_scalars[0] >> 32);
         }
+        tr.mark("resolve");
     }
-    tr.mark("resolve");
     if (!needs_unescape) {  // no 0x5C / 0xFF among the literals: the buffer is already the answer
         *d_out = (uint8_t *)sb.release();
         *out_n = (size_t)sbn;
