@@ -144,6 +144,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
                         cudaStream_t s) {
     ArenaScope scope(s);
     Ctx &c = ctx();
+    Trace tr("hd", s);
     // ---- host: find the first 5C 0A (strings.SplitN, huffman.go:261) and parse the header
     std::vector<uint8_t> h_copy;
     const uint8_t *h = h_in;
@@ -157,27 +158,37 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
     if (h) {
         sp = find_sep(h, n);
     } else {
-        // device-resident input: pull a prefix, then everything if the header is longer
+        // device-resident input: pull a growing prefix until it holds the separator
         size_t take = n < ((size_t)64 << 10) ? n : ((size_t)64 << 10);
+        size_t have = 0;
         for (;;) {
             h_copy.resize(take);
-            RSN_CUDA(cudaMemcpyAsync(h_copy.data(), d_in, take, cudaMemcpyDeviceToHost, s));
+            RSN_CUDA(cudaMemcpyAsync(h_copy.data() + have, d_in + have, take - have, cudaMemcpyDeviceToHost, s));
             RSN_CUDA(cudaStreamSynchronize(s));
-            sp = find_sep(h_copy.data(), take);
-            if (sp >= 0 || take == n) break;
-            take = n;
+            // the separator may straddle the previous chunk boundary: rescan from one byte before it
+            const size_t from = have ? have - 1 : 0;
+            const ptrdiff_t r = find_sep(h_copy.data() + from, take - from);
+            if (r >= 0) {
+                sp = r + (ptrdiff_t)from;
+                break;
+            }
+            if (take == n) break;
+            have = take;
+            take = take * 8 < n ? take * 8 : n;
         }
         h = h_copy.data();
         hn = take;
     }
     (void)hn;
     if (sp < 0) return RSN_ERR_NO_SEPARATOR;
+    tr.mark("find sep");
     std::vector<HuffLeaf> leaves;
     if (!huff_parse_header(h, (size_t)sp, leaves)) return RSN_ERR_BAD_HEADER;
     if (leaves.empty()) return RSN_ERR_BAD_HEADER;  // buildTree on an empty map panics
     HuffTree tree;
     huff_build_tree(leaves, tree);
 
+    tr.mark("header+tree");
     const size_t pay_off = (size_t)sp + 2;
     const size_t pn = n - pay_off;
     uint64_t diff = 0;
@@ -268,6 +279,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
         std::swap(e_prev, e_next);
         if (!(uint32_t)changed) break;
     }
+    tr.mark("init+sync");
     RSN_TRY(spine_scan_u64(cnt.as<uint64_t>(), off.as<uint64_t>(), off.as<uint64_t>() + subs, subs, s));
     uint64_t total = 0;
     RSN_TRY(read_u64(off.as<uint64_t>() + subs, &total, s));
@@ -277,6 +289,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
                flag.as<uint32_t>());
     uint64_t err = 0;
     RSN_TRY(read_u64(flag.as<uint64_t>(), &err, s));
+    tr.mark("write");
     if ((uint32_t)err) return RSN_ERR_TRUNCATED;
     (void)c;
     *d_out = (uint8_t *)out.release();

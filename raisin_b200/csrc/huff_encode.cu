@@ -224,6 +224,7 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     Ctx &c = ctx();
     const size_t tiles = div_up(n, kTile);
 
+    Trace tr("hc", s);
     // ---- histogram
     DevBuf hist, list, count;
     RSN_TRY(hist.alloc((size_t)kRuneSpace * 8, s));
@@ -242,6 +243,7 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     RSN_CUDA(cudaStreamSynchronize(s));
     list.reset();
 
+    tr.mark("hist+d2h");
     // ---- host: tree, codes, header (exactly as the reference builds them)
     std::vector<HuffLeaf> leaves(k);
     for (size_t i = 0; i < k; i++) leaves[i] = HuffLeaf{(int64_t)h_list[i].freq, (int32_t)h_list[i].rune};
@@ -262,6 +264,7 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     const size_t prefix = hdr.size() + 3;  // header, 5C 0A, pad byte
     const size_t total = prefix + payload;
 
+    tr.mark("host tree");
     // ---- device: code tables
     DevBuf code_tab, len_tab, clist;
     RSN_TRY(code_tab.alloc((size_t)kRuneSpace * 8, s));
@@ -289,6 +292,7 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
         RSN_LAUNCH(k_enc_write, (unsigned)tiles, kTileThreads, 0, s, d_in, n, code_tab.as<uint64_t>(),
                    len_tab.as<uint8_t>(), tbo.as<uint64_t>(), (uint64_t)prefix * 8 + pad, out.as<uint32_t>());
     }
+    tr.mark("encode");
     // h_codes / pre are read by async copies: wait before they go out of scope
     RSN_CUDA(cudaStreamSynchronize(s));
     (void)c;

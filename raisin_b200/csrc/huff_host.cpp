@@ -9,13 +9,44 @@
 namespace rsn {
 
 namespace {
-// container/heap (Go 1.15) on an index array; Less compares frequencies only (huffman.go:43-45),
-// so the shape of the tree under ties is fixed by these exact sift rules.
-struct GoHeap {
-    const std::vector<int64_t> &f;
-    std::vector<int32_t> h;
-    explicit GoHeap(const std::vector<int64_t> &freq) : f(freq) {}
-    bool less(int i, int j) const { return f[h[i]] < f[h[j]]; }
+// LSD byte-wise radix sort of 64-bit keys, skipping bytes that are equal in all keys.
+void radix_sort_u64(std::vector<uint64_t> &keys) {
+    const size_t n = keys.size();
+    if (n < 2048) {
+        std::sort(keys.begin(), keys.end());
+        return;
+    }
+    uint64_t all_or = 0, all_and = ~0ull;
+    for (uint64_t k : keys) {
+        all_or |= k;
+        all_and &= k;
+    }
+    const uint64_t varying = all_or ^ all_and;
+    std::vector<uint64_t> tmp(n);
+    uint64_t *src = keys.data(), *dst = tmp.data();
+    for (int byte = 0; byte < 8; byte++) {
+        if (((varying >> (8 * byte)) & 0xFF) == 0) continue;
+        size_t cnt[257] = {0};
+        for (size_t i = 0; i < n; i++) cnt[((src[i] >> (8 * byte)) & 0xFF) + 1]++;
+        for (int d = 0; d < 256; d++) cnt[d + 1] += cnt[d];
+        for (size_t i = 0; i < n; i++) dst[cnt[(src[i] >> (8 * byte)) & 0xFF]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != keys.data()) std::copy(src, src + n, keys.data());
+}
+
+// container/heap (Go 1.15); Less compares frequencies only (huffman.go:43-45), so the shape of
+// the tree under ties is fixed by these exact sift rules.  Entries carry the frequency next to the
+// node index so that sifting does not chase pointers.
+struct HeapEnt {
+    int64_t freq;
+    int32_t node;
+};
+template <typename E, typename Less>
+struct GoHeapT {
+    std::vector<E> h;
+    Less lt;
+    bool less(int i, int j) const { return lt(h[i], h[j]); }
     void up(int j) {
         for (;;) {
             int i = (j - 1) / 2;  // parent; truncating division keeps j == 0 at 0
@@ -39,25 +70,43 @@ struct GoHeap {
         int n = (int)h.size();
         for (int i = n / 2 - 1; i >= 0; i--) down(i, n);
     }
-    int32_t pop() {
+    E pop() {
         int n = (int)h.size() - 1;
         std::swap(h[0], h[n]);
         down(0, n);
-        int32_t v = h.back();
+        E v = h.back();
         h.pop_back();
         return v;
     }
-    void push(int32_t v) {
+    void push(E v) {
         h.push_back(v);
         up((int)h.size() - 1);
     }
 };
+struct LessEnt {
+    bool operator()(const HeapEnt &a, const HeapEnt &b) const { return a.freq < b.freq; }
+};
+// frequency in the high 40 bits, node index in the low 24: half the bytes per sift step
+struct LessPacked {
+    bool operator()(uint64_t a, uint64_t b) const { return (a >> 24) < (b >> 24); }
+};
 }  // namespace
 
 void huff_build_tree(std::vector<HuffLeaf> leaves, HuffTree &t) {
-    std::sort(leaves.begin(), leaves.end(), [](const HuffLeaf &a, const HuffLeaf &b) {
-        return a.freq != b.freq ? a.freq < b.freq : a.rune < b.rune;
-    });
+    // leaves in (freq asc, rune asc) order (huffman.go:64-87)
+    bool packable = true;
+    for (const HuffLeaf &l : leaves)
+        if (l.freq < 0 || l.freq >= ((int64_t)1 << 42)) packable = false;
+    if (packable) {  // one integer key per leaf sorts much faster than a comparator on pairs
+        std::vector<uint64_t> keys(leaves.size());
+        for (size_t i = 0; i < leaves.size(); i++) keys[i] = ((uint64_t)leaves[i].freq << 21) | (uint32_t)leaves[i].rune;
+        radix_sort_u64(keys);
+        for (size_t i = 0; i < leaves.size(); i++) leaves[i] = HuffLeaf{(int64_t)(keys[i] >> 21), (int32_t)(keys[i] & 0x1FFFFFu)};
+    } else {
+        std::sort(leaves.begin(), leaves.end(), [](const HuffLeaf &a, const HuffLeaf &b) {
+            return a.freq != b.freq ? a.freq < b.freq : a.rune < b.rune;
+        });
+    }
     const size_t k = leaves.size();
     t.nodes.clear();
     t.freq.clear();
@@ -68,42 +117,65 @@ void huff_build_tree(std::vector<HuffLeaf> leaves, HuffTree &t) {
         t.nodes.push_back(HuffNode{-1, leaves[i].rune});
         t.freq.push_back(leaves[i].freq);
     }
-    GoHeap hp(t.freq);
+    // all partial sums stay below 2^40 and node indices below 2^24: use the packed heap
+    bool small = 2 * k < ((size_t)1 << 24);
+    if (small) {
+        uint64_t total = 0;
+        for (const HuffLeaf &l : leaves) {
+            if (l.freq < 0 || l.freq >= ((int64_t)1 << 39)) small = false;
+            else total += (uint64_t)l.freq;
+        }
+        if (total >= ((uint64_t)1 << 39)) small = false;
+    }
+    if (small) {
+        GoHeapT<uint64_t, LessPacked> hp;
+        hp.h.resize(k);
+        for (size_t i = 0; i < k; i++) hp.h[i] = ((uint64_t)leaves[i].freq << 24) | (uint64_t)i;
+        hp.init();
+        while (hp.h.size() > 1) {
+            const uint64_t a = hp.pop();
+            const uint64_t b = hp.pop();
+            const uint64_t f = (a >> 24) + (b >> 24);
+            t.nodes.push_back(HuffNode{(int32_t)(a & 0xFFFFFFu), (int32_t)(b & 0xFFFFFFu)});
+            t.freq.push_back((int64_t)f);
+            hp.push((f << 24) | (uint64_t)(t.nodes.size() - 1));
+        }
+        t.root = (int32_t)(hp.h[0] & 0xFFFFFFu);
+        return;
+    }
+    GoHeapT<HeapEnt, LessEnt> hp;
     hp.h.resize(k);
-    for (size_t i = 0; i < k; i++) hp.h[i] = (int32_t)i;
+    for (size_t i = 0; i < k; i++) hp.h[i] = HeapEnt{leaves[i].freq, (int32_t)i};
     hp.init();
     while (hp.h.size() > 1) {
-        int32_t a = hp.pop();
-        int32_t b = hp.pop();
-        t.nodes.push_back(HuffNode{a, b});
-        t.freq.push_back((int64_t)((uint64_t)t.freq[a] + (uint64_t)t.freq[b]));
-        hp.push((int32_t)t.nodes.size() - 1);
+        const HeapEnt a = hp.pop();
+        const HeapEnt b = hp.pop();
+        const int64_t f = (int64_t)((uint64_t)a.freq + (uint64_t)b.freq);  // wraps like Go's int
+        t.nodes.push_back(HuffNode{a.node, b.node});
+        t.freq.push_back(f);
+        hp.push(HeapEnt{f, (int32_t)t.nodes.size() - 1});
     }
-    t.root = hp.h[0];
+    t.root = hp.h[0].node;
 }
 
 bool huff_codes(const HuffTree &t, std::vector<HuffCode> &codes) {
+    // printCodes (huffman.go:110-127): left appends '0', right appends '1'.  Every internal node was
+    // created after its children (larger index), so one sweep from the root down assigns all paths.
+    const size_t nn = t.nodes.size();
+    std::vector<uint64_t> code(nn, 0);
+    std::vector<uint32_t> depth(nn, 0);
+    bool ok = true;
+    for (size_t v = nn; v-- > t.n_leaves;) {
+        const HuffNode &nd = t.nodes[v];
+        code[nd.left] = code[v] << 1;
+        code[nd.right] = (code[v] << 1) | 1;
+        depth[nd.left] = depth[nd.right] = depth[v] + 1;
+    }
     codes.clear();
     codes.reserve(t.n_leaves);
-    struct Item {
-        int32_t node;
-        uint32_t depth;
-        uint64_t code;
-    };
-    std::vector<Item> stack;
-    stack.push_back({t.root, 0, 0});
-    bool ok = true;
-    while (!stack.empty()) {
-        Item it = stack.back();
-        stack.pop_back();
-        const HuffNode &nd = t.nodes[it.node];
-        if (nd.left < 0) {
-            if (it.depth > 64) ok = false;
-            codes.push_back(HuffCode{nd.right, (uint8_t)std::min<uint32_t>(it.depth, 255), it.code, t.freq[it.node]});
-            continue;
-        }
-        stack.push_back({nd.right, it.depth + 1, (it.code << 1) | 1});  // right appends '1'
-        stack.push_back({nd.left, it.depth + 1, it.code << 1});          // left appends '0'
+    for (size_t v = 0; v < t.n_leaves; v++) {
+        if (depth[v] > 64) ok = false;
+        codes.push_back(HuffCode{t.nodes[v].right, (uint8_t)std::min<uint32_t>(depth[v], 255), code[v], t.freq[v]});
     }
     return ok;
 }
@@ -120,7 +192,20 @@ static void put_dec(std::vector<uint8_t> &o, uint64_t v) {
 
 void huff_header(const std::vector<HuffLeaf> &leaves_in, std::vector<uint8_t> &hdr) {
     std::vector<HuffLeaf> lv(leaves_in);
-    std::sort(lv.begin(), lv.end(), [](const HuffLeaf &a, const HuffLeaf &b) { return a.rune < b.rune; });
+    {
+        bool packable = true;
+        for (const HuffLeaf &l : lv)
+            if (l.freq < 0 || l.freq >= ((int64_t)1 << 42)) packable = false;
+        if (packable) {
+            std::vector<uint64_t> keys(lv.size());
+            for (size_t i = 0; i < lv.size(); i++) keys[i] = ((uint64_t)(uint32_t)lv[i].rune << 42) | (uint64_t)lv[i].freq;
+            radix_sort_u64(keys);
+            for (size_t i = 0; i < lv.size(); i++)
+                lv[i] = HuffLeaf{(int64_t)(keys[i] & (((uint64_t)1 << 42) - 1)), (int32_t)(keys[i] >> 42)};
+        } else {
+            std::sort(lv.begin(), lv.end(), [](const HuffLeaf &a, const HuffLeaf &b) { return a.rune < b.rune; });
+        }
+    }
     if (lv.size() >= 2 && lv.back().rune == 0x5C) std::swap(lv[lv.size() - 1], lv[lv.size() - 2]);
     hdr.clear();
     for (const HuffLeaf &l : lv) {
@@ -160,7 +245,16 @@ static int64_t atoi_digits(const std::vector<uint8_t> &d) {
 }
 
 bool huff_parse_header(const uint8_t *h, size_t hn, std::vector<HuffLeaf> &leaves) {
+    // rune -> (freq, seen) with map semantics (the last assignment wins); a dense table beats a hash
+    // map by far when the header has ~1e5 records (binary input)
+    std::vector<int64_t> dense;
+    std::vector<uint8_t> seen;
     std::unordered_map<int32_t, int64_t> m;
+    const bool use_dense = hn > 8192;
+    if (use_dense) {
+        dense.assign(0x110000, 0);
+        seen.assign(0x110000, 0);
+    }
     std::vector<int32_t> order;
     std::vector<uint8_t> temp;
     for (size_t i = 0; i < hn; i++) {
@@ -185,12 +279,21 @@ bool huff_parse_header(const uint8_t *h, size_t hn, std::vector<HuffLeaf> &leave
             const uint8_t b1 = p + 1 < hn ? h[p + 1] : 0, b2 = p + 2 < hn ? h[p + 2] : 0, b3 = p + 3 < hn ? h[p + 3] : 0;
             utf8_decode_at(h[p], b1, b2, b3, hn - p, &sym);
         }
-        if (m.find(sym) == m.end()) order.push_back(sym);
-        m[sym] = f;
+        if (use_dense) {
+            if (!seen[sym]) {
+                seen[sym] = 1;
+                order.push_back(sym);
+            }
+            dense[sym] = f;
+        } else {
+            if (m.find(sym) == m.end()) order.push_back(sym);
+            m[sym] = f;
+        }
         i++;
     }
     leaves.clear();
-    for (int32_t r : order) leaves.push_back(HuffLeaf{m[r], r});
+    leaves.reserve(order.size());
+    for (int32_t r : order) leaves.push_back(HuffLeaf{use_dense ? dense[r] : m[r], r});
     return true;
 }
 
