@@ -42,6 +42,24 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def k2_traffic(n):
+    """DRAM bytes of one K2 launch from the committed ncu --set full capture (per launch)."""
+    p = os.path.join(ROOT, "profiles", "r1_k2_ncu_full.md")
+    try:
+        rd = wr = None
+        for line in open(p):
+            parts = line.split()
+            if line.startswith("dram__bytes_read.sum"):
+                rd = float(parts[1]) * (1e6 if parts[2].startswith("Mbyte") else 1e9 if parts[2].startswith("Gbyte") else 1e3 if parts[2].startswith("Kbyte") else 1)
+            if line.startswith("dram__bytes_write.sum"):
+                wr = float(parts[1]) * (1e6 if parts[2].startswith("Mbyte") else 1e9 if parts[2].startswith("Gbyte") else 1e3 if parts[2].startswith("Kbyte") else 1)
+        if rd is None or wr is None:
+            return None
+        return int((rd + wr) * n / N_BYTES)
+    except OSError:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
 
@@ -423,7 +441,9 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "lzss match search (K2)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": k2_traffic(n), "peak_source": peak_src,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_match_tile launch on the "
+                                       "64 MiB stream, profiles/r1_k2_ncu_full.md (scaled by n if --bytes differs)",
                      "kernel_ms": k2_ms, "algorithmic_bytes": algo_bytes_k2,
                      "note": "K2 is integer/shared-memory bound, not HBM bound; see DESIGN.md"},
     }
