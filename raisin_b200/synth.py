@@ -25,6 +25,8 @@ def _vocab(rng: np.random.Generator, words: int = 4096):
 
 def text(n: int, seed: int = 1) -> bytes:
     """English-like text: 4096-word Zipf(1.0) vocabulary, sentences of 5-20 words, LF ~ every 80 chars."""
+    if n <= 0:
+        return b""
     rng = np.random.default_rng(seed)
     chars, offs, lens = _vocab(rng)
     words = len(lens)
