@@ -95,15 +95,56 @@ using namespace rsn;
 
 extern "C" {
 
+// Large inputs: the host->device copy is cut into chunks on a second stream and the match search
+// of a chunk starts as soon as the chunk after it has landed (it needs a window of look-ahead).
+// The search runs on the raw bytes, which is only right when nothing needs escaping; that is known
+// once the whole input is on the device, and otherwise the speculative arrays are dropped.
+static int lzss_compress_overlapped(const uint8_t *in, size_t n, int64_t window, int variant, uint8_t **r, size_t *rn,
+                                    cudaStream_t s) {
+    Ctx &c = ctx();
+    const size_t T = lzss_match_tile_size();
+    const size_t chunk = (size_t)8 << 20;  // multiple of the tile size
+    const size_t chunks = div_up(n, chunk);
+    uint32_t W = 0;
+    RSN_TRY(lzss_effective_window(window, n, &W));
+    DevBuf d, packed;
+    RSN_TRY(d.alloc(n + 64, s));
+    RSN_TRY(packed.alloc(div_up(n, 4096) * 4096 * 4 + 64, s));
+    // the arena memory may still be read by work queued on s: order the copies after it
+    RSN_CUDA(cudaEventRecord(c.chunk_ev[63], s));
+    RSN_CUDA(cudaStreamWaitEvent(c.copy_stream, c.chunk_ev[63], 0));
+    auto copy_chunk = [&](size_t k) -> int {
+        const size_t lo = k * chunk, len = std::min(chunk, n - lo);
+        RSN_CUDA(cudaMemcpyAsync(d.as<uint8_t>() + lo, in + lo, len, cudaMemcpyHostToDevice, c.copy_stream));
+        RSN_CUDA(cudaEventRecord(c.chunk_ev[k], c.copy_stream));
+        return RSN_OK;
+    };
+    const size_t tiles = div_up(n, T), tiles_per_chunk = chunk / T;
+    RSN_TRY(copy_chunk(0));
+    for (size_t k = 0; k < chunks; k++) {
+        if (k + 1 < chunks) RSN_TRY(copy_chunk(k + 1));  // interleaved so pageable sources overlap too
+        // tiles of chunk k need bytes up to their end + W: wait for chunk k+1 (or the last one)
+        RSN_CUDA(cudaStreamWaitEvent(s, c.chunk_ev[std::min(k + 1, chunks - 1)], 0));
+        const size_t t_lo = k * tiles_per_chunk, t_hi = std::min(tiles, t_lo + tiles_per_chunk);
+        RSN_TRY(lzss_match_tile_range(d.as<uint8_t>(), n, W, packed.as<uint32_t>(), t_lo, t_hi, k + 1 == chunks, s));
+    }
+    return lzss_compress_dev_ex(d.as<uint8_t>(), n, window, variant, packed.as<uint32_t>(), r, rn, s);
+}
+
 int rsn_lzss_compress(const uint8_t *in, size_t n, int64_t window, int variant, uint8_t **out, size_t *out_n) {
     if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());
     cudaStream_t s = ctx().own_stream;
     ArenaScope scope(s);
-    DevBuf d;
-    RSN_TRY(to_device(in, n, d, s));
     uint8_t *r = nullptr;
     size_t rn = 0;
+    const bool tile_window = window > 0 && window <= 4096;
+    if (tile_window && n >= ((size_t)16 << 20) && n <= ((size_t)8 << 20) * 60) {
+        RSN_TRY(lzss_compress_overlapped(in, n, window, variant, &r, &rn, s));
+        return to_host(r, rn, out, out_n, s);
+    }
+    DevBuf d;
+    RSN_TRY(to_device(in, n, d, s));
     RSN_TRY(lzss_compress_dev(d.as<uint8_t>(), n, window, variant, &r, &rn, s));
     return to_host(r, rn, out, out_n, s);
 }

@@ -14,6 +14,8 @@ namespace rsn {
 struct Ctx {
     int device = -1;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host->device chunks that overlap the first kernels
+    cudaEvent_t chunk_ev[64] = {nullptr};
     bool ready = false;
     uint64_t launches = 0;
     char cuda_err[256] = {0};

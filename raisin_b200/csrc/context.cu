@@ -38,6 +38,9 @@ static int init_ctx(int device) {
     if (c.ready && c.device == device) return RSN_OK;
     c.device = device;
     if (!c.own_stream) RSN_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    if (!c.copy_stream) RSN_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    for (auto &e : c.chunk_ev)
+        if (!e) RSN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (!c.h_scalars) RSN_CUDA(cudaHostAlloc((void **)&c.h_scalars, 64 * sizeof(uint64_t), cudaHostAllocDefault));
     c.ready = true;
     return RSN_OK;
@@ -455,6 +458,16 @@ void rsn_shutdown(void) {
         cudaStreamDestroy(c.own_stream);
         c.own_stream = nullptr;
     }
+    if (c.copy_stream) {
+        cudaStreamSynchronize(c.copy_stream);
+        cudaStreamDestroy(c.copy_stream);
+        c.copy_stream = nullptr;
+    }
+    for (auto &e : c.chunk_ev)
+        if (e) {
+            cudaEventDestroy(e);
+            e = nullptr;
+        }
     if (c.h_scalars) {
         cudaFreeHost(c.h_scalars);
         c.h_scalars = nullptr;

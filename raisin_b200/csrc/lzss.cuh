@@ -12,10 +12,16 @@ constexpr uint32_t kMaxWindow = 32768;
 int lzss_match(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, cudaStream_t s);
 
 int lzss_match_tile(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, cudaStream_t s);
+int lzss_match_tile_range(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, size_t tile_lo,
+                          size_t tile_hi, bool run_fix0, cudaStream_t s);
+size_t lzss_match_tile_size();
 int lzss_effective_window(int64_t window, size_t enc_n, uint32_t *W);
 int lzss_escape(const uint8_t *d_in, size_t n, DevBuf &enc, const uint8_t **enc_ptr, size_t *enc_n, cudaStream_t s);
 int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant, uint8_t **d_out, size_t *out_n,
                       cudaStream_t s);
+// `spec_packed`: match arrays already computed over d_in itself (valid iff nothing needed escaping)
+int lzss_compress_dev_ex(const uint8_t *d_in, size_t n, int64_t window, int variant, uint32_t *spec_packed,
+                         uint8_t **d_out, size_t *out_n, cudaStream_t s);
 int lzss_emit_dev(const uint8_t *d_enc, size_t n, int64_t window, int variant, const uint32_t *d_packed,
                   uint8_t **d_out, size_t *out_n, cudaStream_t s);
 int lzss_escape_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s);

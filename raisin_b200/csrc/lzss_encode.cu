@@ -620,6 +620,11 @@ int lzss_escape_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_
 
 int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant, uint8_t **d_out, size_t *out_n,
                       cudaStream_t s) {
+    return lzss_compress_dev_ex(d_in, n, window, variant, nullptr, d_out, out_n, s);
+}
+
+int lzss_compress_dev_ex(const uint8_t *d_in, size_t n, int64_t window, int variant, uint32_t *spec_packed,
+                         uint8_t **d_out, size_t *out_n, cudaStream_t s) {
     ArenaScope scope(s);
     if (variant != RSN_LZSS_ASYNC && variant != RSN_LZSS_ITER) return RSN_ERR_INVALID_ARG;
     DevBuf enc_buf;
@@ -636,8 +641,12 @@ int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant
     uint32_t W = 0;
     RSN_TRY(lzss_effective_window(window, en, &W));
     DevBuf lo, sbits, fp;
-    RSN_TRY(lo.alloc(div_up(en, kPB) * kPB * 4 + 64, s));
-    RSN_TRY(lzss_match(enc, en, W, lo.as<uint32_t>(), s));
+    uint32_t *packed = spec_packed;
+    if (!(spec_packed && enc == d_in)) {  // no usable speculative arrays: search now
+        RSN_TRY(lo.alloc(div_up(en, kPB) * kPB * 4 + 64, s));
+        RSN_TRY(lzss_match(enc, en, W, lo.as<uint32_t>(), s));
+        packed = lo.as<uint32_t>();
+    }
     ParseCfg cfg{W, W, variant, nullptr};
     if (variant == RSN_LZSS_ITER) {
         cfg.J = W + 1;
@@ -651,7 +660,7 @@ int lzss_compress_dev(const uint8_t *d_in, size_t n, int64_t window, int variant
                    sbits.as<uint32_t>());
         cfg.sbits = sbits.as<uint32_t>();
     }
-    return parse_and_emit(enc, en, cfg, lo.as<uint32_t>(), d_out, out_n, s);
+    return parse_and_emit(enc, en, cfg, packed, d_out, out_n, s);
 }
 
 }  // namespace rsn

@@ -192,14 +192,14 @@ __device__ __forceinline__ void slot_range(const Smem &sm, const uint16_t *arr, 
 }  // namespace tile
 
 __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
-                                                              uint32_t *__restrict__ packed) {
+                                                              uint32_t *__restrict__ packed, size_t first_tile) {
     using namespace tile;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     uint8_t *s = reinterpret_cast<uint8_t *>(sm.s_words);
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
-    const size_t tile_start = (size_t)blockIdx.x * T;
+    const size_t tile_start = (first_tile + blockIdx.x) * T;
     const uint32_t tile_len = (uint32_t)min((size_t)T, n - tile_start);
     const size_t base = tile_start > (size_t)W + 2 ? ((tile_start - W - 2) & ~(size_t)15) : 0;  // 16-byte aligned
     const uint32_t halo = (uint32_t)(tile_start - base);
@@ -452,9 +452,27 @@ int lzss_match_tile(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_pack
         RSN_CUDA(cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    RSN_LAUNCH(k_match_tile, (unsigned)div_up(n, tile::T), tile::THREADS, smem, s, d_enc, n, W, d_packed);
+    RSN_LAUNCH(k_match_tile, (unsigned)div_up(n, tile::T), tile::THREADS, smem, s, d_enc, n, W, d_packed, (size_t)0);
     RSN_LAUNCH(k_match_tile_fix0, (unsigned)div_up(min(n, (size_t)W + 2), 128), 128, 0, s, d_enc, n, W, d_packed);
     return RSN_OK;
 }
+
+// Tiles [tile_lo, tile_hi) only (positions tile*T ...); the caller guarantees that the bytes up to
+// min(n, tile_hi*T + W) are in place.  fix0 must be run once tile 0 and tile 1 are done.
+int lzss_match_tile_range(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, size_t tile_lo,
+                          size_t tile_hi, bool run_fix0, cudaStream_t s) {
+    static thread_local bool attr_set = false;
+    const size_t smem = sizeof(tile::Smem);
+    if (!attr_set) {
+        RSN_CUDA(cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (tile_hi > tile_lo)
+        RSN_LAUNCH(k_match_tile, (unsigned)(tile_hi - tile_lo), tile::THREADS, smem, s, d_enc, n, W, d_packed, tile_lo);
+    if (run_fix0)
+        RSN_LAUNCH(k_match_tile_fix0, (unsigned)div_up(min(n, (size_t)W + 2), 128), 128, 0, s, d_enc, n, W, d_packed);
+    return RSN_OK;
+}
+size_t lzss_match_tile_size() { return tile::T; }
 
 }  // namespace rsn

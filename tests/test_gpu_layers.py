@@ -115,3 +115,40 @@ def test_cli_rsn_interchange(rsn, oracle, tmp_path):
     e.write_bytes(b"")
     out = subprocess.check_output([cli, "-benchmark", "-algorithm=huffman", str(e)], text=True)
     assert "DNF" in out
+
+
+def test_layer_orders_and_single_layers(rsn, oracle):
+    data = synth.text(50000, 13) + b"<tag>\\n" * 20
+    for algos in (["lzss"], ["huffman"], ["huffman", "lzss"], ["lzss", "lzss"], ["lzss", "huffman"]):
+        want = data
+        for a in algos:
+            want = oracle.lzss_compress_async(want, 4096) if a == "lzss" else oracle.huff_compress(want)
+        got = rsn.engine.compress_fused(data, algos)
+        assert got == want, algos
+        assert rsn.engine.compress(data, algos) == want, algos
+        back = want
+        for a in reversed(algos):
+            back = oracle.lzss_decompress(back) if a == "lzss" else oracle.huff_decompress(back)
+        assert rsn.engine.decompress_fused(got, algos) == back, algos
+
+
+def test_batch_device_buffers(rsn, oracle):
+    """rsn_batch_layers with device-resident inputs and outputs."""
+    import ctypes as C
+
+    import torch
+
+    lib = rsn._lib.lib()
+    files = [synth.batch_file(j, 40000) for j in range(9)]
+    tens = [torch.frombuffer(bytearray(f), dtype=torch.uint8).cuda() for f in files]
+    torch.cuda.synchronize()
+    n = len(files)
+    ins = (C.c_void_p * n)(*[t.data_ptr() for t in tens])
+    ns = (C.c_size_t * n)(*[len(f) for f in files])
+    outs, out_ns, rcs = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+    rsn._lib.check(lib.rsn_batch_layers(b"lzss,huffman", 1, n, ins, ns, outs, out_ns, rcs, 4, 1))
+    for i, f in enumerate(files):
+        h = (C.c_uint8 * out_ns[i])()
+        rsn._lib.check(lib.rsn_dev_download(outs[i], out_ns[i], h, None))
+        assert bytes(h) == oracle.huff_compress(oracle.lzss_compress_async(f, 4096))
+        lib.rsn_dev_free(outs[i], None)
