@@ -152,3 +152,30 @@ def test_batch_device_buffers(rsn, oracle):
         rsn._lib.check(lib.rsn_dev_download(outs[i], out_ns[i], h, None))
         assert bytes(h) == oracle.huff_compress(oracle.lzss_compress_async(f, 4096))
         lib.rsn_dev_free(outs[i], None)
+
+
+def test_concurrent_callers(rsn, oracle):
+    """engine.BenchmarkSuite calls the codecs from several goroutines at once (engine.go:235-244):
+    the C ABI must be re-entrant from multiple OS threads (ctypes releases the GIL during calls)."""
+    import threading
+
+    inputs = [synth.mixed(120000 + 7919 * k, 50 + k, segment=30000) for k in range(6)]
+    want = [oracle.huff_compress(oracle.lzss_compress_async(d, 4096)) for d in inputs]
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(4):
+                got = rsn.engine.compress(inputs[k], ALGOS)
+                assert got == want[k]
+                back = rsn.engine.decompress(got, ALGOS)
+                assert back == oracle.lzss_decompress(oracle.huff_decompress(want[k]))
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(inputs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
