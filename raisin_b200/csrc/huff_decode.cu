@@ -30,14 +30,69 @@ struct DecParams {
     int32_t root;
 };
 
-// the 32 stream bits starting at code bit i, MSB first (bytes are big-endian bit order in memory)
-__device__ __forceinline__ uint32_t peek32(const DecParams &p, uint64_t i) {
-    const uint64_t b = p.bit0 + i;
+// Forward bit reader over the big-endian payload: `buf` holds the next `avail` stream bits in its
+// high end (MSB first); refilled 32 bits at a time from aligned words.
+struct BitReader {
+    const uint32_t *words;
+    uint64_t nwords, next;  // next word index to append
+    uint64_t buf;
+    uint32_t avail;
+    __device__ __forceinline__ uint32_t word(uint64_t w) const {
+        return w < nwords ? __byte_perm(__ldg(words + w), 0, 0x0123) : 0u;
+    }
+    __device__ __forceinline__ void seek(const DecParams &p, uint64_t pos);
+    __device__ __forceinline__ void refill() {
+        if (avail <= 32) {
+            buf |= (uint64_t)word(next) << (32 - avail);
+            avail += 32;
+            next++;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int bits) const { return (uint32_t)(buf >> (64 - bits)); }
+    __device__ __forceinline__ void skip(uint32_t bits) {
+        buf <<= bits;
+        avail -= bits;
+    }
+};
+
+__device__ __forceinline__ void BitReader::seek(const DecParams &p, uint64_t pos) {
+    words = p.words;
+    nwords = p.nwords;
+    const uint64_t b = p.bit0 + pos;
     const uint64_t w = b >> 5;
-    const uint32_t hi = w < p.nwords ? __byte_perm(__ldg(p.words + w), 0, 0x0123) : 0u;
-    const uint32_t lo = w + 1 < p.nwords ? __byte_perm(__ldg(p.words + w + 1), 0, 0x0123) : 0u;
-    return __funnelshift_l(lo, hi, (uint32_t)(b & 31));
+    const uint32_t sh = (uint32_t)(b & 31);
+    buf = (((uint64_t)word(w) << 32) | (uint64_t)word(w + 1)) << sh;
+    avail = 64 - sh;
+    next = w + 2;
 }
+
+// UTF-8 bytes to a byte address with word stores once the address is 4-byte aligned.
+struct ByteWriter {
+    uint8_t *p;
+    uint32_t acc;  // pending bytes, little-endian
+    uint32_t k;    // number of pending bytes (only while p is 4-byte aligned)
+    __device__ __forceinline__ void init(uint8_t *dst) {
+        p = dst;
+        acc = 0;
+        k = 0;
+    }
+    __device__ __forceinline__ void put(uint8_t b) {
+        if (k == 0 && (reinterpret_cast<uintptr_t>(p) & 3)) {
+            *p++ = b;  // unaligned head
+            return;
+        }
+        acc |= (uint32_t)b << (8 * k);
+        if (++k == 4) {
+            *reinterpret_cast<uint32_t *>(p) = acc;
+            p += 4;
+            acc = 0;
+            k = 0;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        for (uint32_t i = 0; i < k; i++) p[i] = (uint8_t)(acc >> (8 * i));
+    }
+};
 
 // Decode codes that START in [pos, limit).  Returns the position after the last complete code
 // (>= limit unless the bits ran out).  `truncated` is set if the bits end inside a code.
@@ -47,43 +102,60 @@ __device__ __forceinline__ uint64_t decode_span(const DecParams &p, uint64_t pos
                                                 bool &truncated, uint8_t *out) {
     bytes = 0;
     truncated = false;
+    BitReader br;
+    br.seek(p, pos);
+    ByteWriter bw;
+    if (WRITE) bw.init(out);
     while (pos < limit) {
-        const uint32_t win = peek32(p, pos);
-        const uint32_t ent = __ldg(p.lut + (win >> (32 - kLutBits)));
+        br.refill();
+        const uint32_t ent = __ldg(p.lut + br.peek(kLutBits));
         int32_t rune;
-        uint64_t q;
         if (ent >> 31) {
             const uint32_t len = (ent >> 21) & 0x3FFu;
-            q = pos + len;
-            if (q > p.max) {  // the code would need bits past the end (huffman.go:145)
+            if (pos + len > p.max) {  // the code would need bits past the end (huffman.go:145)
                 truncated = true;
-                return p.max;
+                pos = p.max;
+                break;
             }
+            br.skip(len);
+            pos += len;
             rune = (int32_t)(ent & 0x1FFFFFu);
         } else {  // longer than the table: finish on the tree
             int32_t node = (int32_t)ent;
-            q = pos + kLutBits;
-            if (q > p.max) {
+            if (pos + kLutBits > p.max) {
                 truncated = true;
-                return p.max;
+                pos = p.max;
+                break;
             }
+            br.skip(kLutBits);
+            pos += kLutBits;
             HuffNode nd = p.nodes[node];
             while (nd.left >= 0) {
-                if (q >= p.max) {
+                if (pos >= p.max) {
                     truncated = true;
-                    return q;
+                    break;
                 }
-                const uint32_t bit = peek32(p, q) >> 31;
-                node = bit ? nd.right : nd.left;
+                br.refill();
+                node = br.peek(1) ? nd.right : nd.left;
+                br.skip(1);
                 nd = p.nodes[node];
-                q++;
+                pos++;
             }
+            if (truncated) break;
             rune = nd.right;
         }
-        if (WRITE) bytes += (uint64_t)utf8_encode(rune, out + bytes);
-        else bytes += (uint64_t)utf8_width(rune);
-        pos = q;
+        if (WRITE) {
+            uint8_t u[4];
+            const int w = utf8_encode(rune, u);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < w) bw.put(u[i]);
+            bytes += (uint64_t)w;
+        } else {
+            bytes += (uint64_t)utf8_width(rune);
+        }
     }
+    if (WRITE) bw.finish();
     return pos;
 }
 

@@ -9,6 +9,7 @@
 #include "huff_host.h"
 #include "utf8.cuh"
 
+#include <algorithm>
 #include <vector>
 
 namespace rsn {
@@ -28,31 +29,63 @@ __device__ __forceinline__ void load_chunk_halo(const uint8_t *__restrict__ in, 
     for (int q = 0; q < 3; q++) w[19 + q] = base + 16 + q < n ? __ldg(in + base + 16 + q) : 0;
 }
 
+// The rune starts of a thread's 16 bytes.  Fast path: a chunk of pure ASCII bytes (< 0x80) needs no
+// neighbours: a byte outside [80,BF] always starts a rune and an ASCII byte is that rune.
+// Returns the mask of starts; runes[k] is set for each start.
+__device__ __forceinline__ uint32_t classify16(const uint8_t *__restrict__ in, size_t base, size_t n, int valid,
+                                               int32_t (&runes)[16]) {
+    uint32_t startmask = 0;
+    if (valid == 16 && ((reinterpret_cast<uintptr_t>(in + base) & 15) == 0)) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(in + base));
+        if (((q.x | q.y | q.z | q.w) & 0x80808080u) == 0) {
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 16; k++) runes[k] = (int32_t)((w[k >> 2] >> ((k & 3) * 8)) & 0xFFu);
+            return 0xFFFFu;
+        }
+    }
+    uint8_t w[22];
+    load_chunk_halo(in, base, n, w);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        runes[k] = 0;
+        if (k < valid) {
+            int32_t r;
+            if (utf8_start_at(w, k, base + k, n, &r)) {
+                startmask |= 1u << k;
+                runes[k] = r;
+            }
+        }
+    }
+    return startmask;
+}
+
 // ============================================================================= K8/K9 histogram
+
+constexpr int kHistCopies = 8;  // replicated shared bins: lanes of a warp spread over copies
 
 __global__ void __launch_bounds__(kTileThreads) k_rune_hist(const uint8_t *__restrict__ in, size_t n, size_t tiles,
                                                             unsigned long long *__restrict__ hist) {
-    __shared__ uint32_t bins[kSmallBins];
+    __shared__ uint32_t bins[kHistCopies][kSmallBins];
     __shared__ uint32_t fffd_sm;
-    for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x) bins[i] = 0;
+    for (int i = threadIdx.x; i < kHistCopies * kSmallBins; i += blockDim.x) (&bins[0][0])[i] = 0;
     if (threadIdx.x == 0) fffd_sm = 0;
     __syncthreads();
+    uint32_t *mybins = bins[threadIdx.x & (kHistCopies - 1)];
     uint32_t fffd = 0;
     for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const size_t base = tile * kTile + (size_t)threadIdx.x * kItems;
         if (base >= n) continue;
-        uint8_t w[22];
-        load_chunk_halo(in, base, n, w);
         const int valid = (int)min((size_t)16, n - base);
+        int32_t runes[16];
+        const uint32_t startmask = classify16(in, base, n, valid, runes);
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            if (k < valid) {
-                int32_t r;
-                if (utf8_start_at(w, k, base + k, n, &r)) {
-                    if (r < kSmallBins) atomicAdd(&bins[r], 1u);
-                    else if (r == 0xFFFD) fffd++;
-                    else atomicAdd(&hist[r], 1ull);
-                }
+            if (startmask & (1u << k)) {
+                const int32_t r = runes[k];
+                if (r < kSmallBins) atomicAdd(&mybins[r], 1u);
+                else if (r == 0xFFFD) fffd++;
+                else atomicAdd(&hist[r], 1ull);
             }
         }
     }
@@ -60,8 +93,12 @@ __global__ void __launch_bounds__(kTileThreads) k_rune_hist(const uint8_t *__res
     for (int d = 16; d; d >>= 1) fffd += __shfl_down_sync(0xffffffffu, fffd, d);
     if (lane_id() == 0 && fffd) atomicAdd(&fffd_sm, fffd);
     __syncthreads();
-    for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x)
-        if (bins[i]) atomicAdd(&hist[i], (unsigned long long)bins[i]);
+    for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int c = 0; c < kHistCopies; c++) v += bins[c][i];
+        if (v) atomicAdd(&hist[i], (unsigned long long)v);
+    }
     if (threadIdx.x == 0 && fffd_sm) atomicAdd(&hist[0xFFFD], (unsigned long long)fffd_sm);
 }
 
@@ -109,16 +146,12 @@ __global__ void __launch_bounds__(kTileThreads) k_enc_count(const uint8_t *__res
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
     uint32_t bits = 0;
     if (base < n) {
-        uint8_t w[22];
-        load_chunk_halo(in, base, n, w);
         const int valid = (int)min((size_t)16, n - base);
+        int32_t runes[16];
+        const uint32_t startmask = classify16(in, base, n, valid, runes);
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (k < valid) {
-                int32_t r;
-                if (utf8_start_at(w, k, base + k, n, &r)) bits += r < kSmallBins ? slen[r] : __ldg(len_tab + r);
-            }
-        }
+        for (int k = 0; k < 16; k++)
+            if (startmask & (1u << k)) bits += runes[k] < kSmallBins ? slen[runes[k]] : __ldg(len_tab + runes[k]);
     }
     uint32_t total;
     block_exclusive_sum<uint32_t>(bits, sm, total);
@@ -165,36 +198,42 @@ struct BitWriter {
     }
 };
 
+// PACKED: every code is at most 24 bits long; runes < 256 then come from a shared table of
+// (len << 24 | code) words and the bits of a thread are assembled in one 64-bit register.
+template <bool PACKED>
 __global__ void __launch_bounds__(kTileThreads) k_enc_write(const uint8_t *__restrict__ in, size_t n,
                                                             const uint64_t *__restrict__ code_tab,
                                                             const uint8_t *__restrict__ len_tab,
                                                             const uint64_t *__restrict__ tile_bitoff,
                                                             uint64_t bit_base, uint32_t *__restrict__ out) {
-    __shared__ uint8_t slen[kSmallBins];
-    __shared__ uint64_t scode[kSmallBins];
+    __shared__ uint8_t slen[PACKED ? 1 : kSmallBins];
+    __shared__ uint64_t scode[PACKED ? 1 : kSmallBins];
+    __shared__ uint32_t spack[PACKED ? kSmallBins : 1];
     __shared__ uint32_t sm[33];
     for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x) {
-        slen[i] = len_tab[i];
-        scode[i] = code_tab[i];
+        if (PACKED) {
+            spack[i] = ((uint32_t)len_tab[i] << 24) | (uint32_t)code_tab[i];
+        } else {
+            slen[i] = len_tab[i];
+            scode[i] = code_tab[i];
+        }
     }
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
-    uint8_t w[22];
-    int valid = 0;
-    uint32_t bits = 0;
-    uint32_t startmask = 0;
+    uint32_t bits = 0, startmask = 0;
     int32_t runes[16];
+    uint32_t ent[PACKED ? 16 : 1];
     if (base < n) {
-        load_chunk_halo(in, base, n, w);
-        valid = (int)min((size_t)16, n - base);
+        const int valid = (int)min((size_t)16, n - base);
+        startmask = classify16(in, base, n, valid, runes);
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            runes[k] = 0;
-            if (k < valid) {
-                int32_t r;
-                if (utf8_start_at(w, k, base + k, n, &r)) {
-                    startmask |= 1u << k;
-                    runes[k] = r;
+            if (startmask & (1u << k)) {
+                const int32_t r = runes[k];
+                if (PACKED) {
+                    ent[k] = r < kSmallBins ? spack[r] : (((uint32_t)__ldg(len_tab + r) << 24) | (uint32_t)__ldg(code_tab + r));
+                    bits += ent[k] >> 24;
+                } else {
                     bits += r < kSmallBins ? slen[r] : __ldg(len_tab + r);
                 }
             }
@@ -203,8 +242,36 @@ __global__ void __launch_bounds__(kTileThreads) k_enc_write(const uint8_t *__res
     uint32_t total;
     const uint32_t pre = block_exclusive_sum<uint32_t>(bits, sm, total);
     if (!startmask) return;
+    const uint64_t bitpos = bit_base + tile_bitoff[blockIdx.x] + pre;
+    if (PACKED) {
+        // acc holds `nb` pending bits in its low end; the first word may be shared with the previous
+        // writer (its bits before `bitpos` stay zero here and are merged with atomicOr)
+        uint64_t word = bitpos >> 5;
+        uint32_t nb = (uint32_t)(bitpos & 31);
+        uint64_t acc = 0;
+        bool first = nb != 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (startmask & (1u << k)) {
+                const uint32_t len = ent[k] >> 24;
+                acc = (acc << len) | (uint64_t)(ent[k] & 0xFFFFFFu);
+                nb += len;
+                if (nb >= 32) {
+                    const uint32_t w32 = (uint32_t)(acc >> (nb - 32));
+                    const uint32_t be = __byte_perm(w32, 0, 0x0123);  // big-endian bit order in memory
+                    if (first) atomicOr(out + word, be);
+                    else out[word] = be;
+                    first = false;
+                    word++;
+                    nb -= 32;
+                }
+            }
+        }
+        if (nb) atomicOr(out + word, __byte_perm((uint32_t)(acc << (32 - nb)), 0, 0x0123));
+        return;
+    }
     BitWriter bw;
-    bw.init(out, bit_base + tile_bitoff[blockIdx.x] + pre);
+    bw.init(out, bitpos);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         if (startmask & (1u << k)) {
@@ -255,9 +322,11 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     huff_header(leaves, hdr);
     std::vector<CodeEntry> h_codes(codes.size());
     uint64_t total_bits = 0;
+    uint32_t maxlen = 0;
     for (size_t i = 0; i < codes.size(); i++) {
         h_codes[i] = CodeEntry{(uint32_t)codes[i].rune, codes[i].len, codes[i].code};
         total_bits += (uint64_t)codes[i].len * (uint64_t)codes[i].freq;
+        maxlen = std::max<uint32_t>(maxlen, codes[i].len);
     }
     const uint32_t pad = (uint32_t)((8 - total_bits % 8) % 8);  // huffman.go:245-249
     const size_t payload = (size_t)((total_bits + pad) / 8);
@@ -289,8 +358,12 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
         RSN_TRY(tbo.alloc((tiles + 1) * 8, s));
         RSN_LAUNCH(k_enc_count, (unsigned)tiles, kTileThreads, 0, s, d_in, n, len_tab.as<uint8_t>(), tb.as<uint64_t>());
         RSN_TRY(spine_scan_u64(tb.as<uint64_t>(), tbo.as<uint64_t>(), tbo.as<uint64_t>() + tiles, tiles, s));
-        RSN_LAUNCH(k_enc_write, (unsigned)tiles, kTileThreads, 0, s, d_in, n, code_tab.as<uint64_t>(),
-                   len_tab.as<uint8_t>(), tbo.as<uint64_t>(), (uint64_t)prefix * 8 + pad, out.as<uint32_t>());
+        if (maxlen <= 24)
+            RSN_LAUNCH(k_enc_write<true>, (unsigned)tiles, kTileThreads, 0, s, d_in, n, code_tab.as<uint64_t>(),
+                       len_tab.as<uint8_t>(), tbo.as<uint64_t>(), (uint64_t)prefix * 8 + pad, out.as<uint32_t>());
+        else
+            RSN_LAUNCH(k_enc_write<false>, (unsigned)tiles, kTileThreads, 0, s, d_in, n, code_tab.as<uint64_t>(),
+                       len_tab.as<uint8_t>(), tbo.as<uint64_t>(), (uint64_t)prefix * 8 + pad, out.as<uint32_t>());
     }
     tr.mark("encode");
     // h_codes / pre are read by async copies: wait before they go out of scope
