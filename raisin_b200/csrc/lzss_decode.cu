@@ -292,14 +292,9 @@ constexpr int kHops = 64;
 // are safe.  Literal bytes (dist == 0) are never written here.
 // `work` == nullptr: first round, one thread per output byte; unfinished bytes are appended to
 // `work_out`.  Later rounds walk the previous round's list only.
-__global__ void __launch_bounds__(256) k_resolve(uint8_t *__restrict__ sb, uint32_t *__restrict__ dist, size_t n,
-                                                 const uint32_t *__restrict__ work, uint32_t *__restrict__ work_out,
-                                                 uint32_t *__restrict__ work_count) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const size_t o = work ? work[t] : t;
-    uint32_t d = dist[o];
-    if (d == 0) return;
+__device__ __forceinline__ void resolve_one(uint8_t *__restrict__ sb, uint32_t *__restrict__ dist, size_t o,
+                                            uint32_t d, uint32_t *__restrict__ work_out,
+                                            uint32_t *__restrict__ work_count) {
     size_t p = o - d;
     int hops = 0;
     uint32_t dp;
@@ -314,6 +309,44 @@ __global__ void __launch_bounds__(256) k_resolve(uint8_t *__restrict__ sb, uint3
         work_out[atomicAdd(work_count, 1u)] = (uint32_t)o;  // rare: chains deeper than kHops
     }
     if (hops) dist[o] = (uint32_t)(o - p);
+}
+
+// First round.  A CTA walks a contiguous chunk of the output front to back, four bytes per thread
+// per step (one 16-byte load of their distances): sources lie a window back, i.e. in lines this
+// same SM loaded a few steps earlier, so the chase mostly hits L1 instead of going to L2.
+constexpr int kResolveChunk = 32768;
+
+__global__ void __launch_bounds__(256) k_resolve4(uint8_t *__restrict__ sb, uint32_t *__restrict__ dist, size_t n,
+                                                  uint32_t *__restrict__ work_out, uint32_t *__restrict__ work_count) {
+    const size_t c_lo = (size_t)blockIdx.x * kResolveChunk;
+    const size_t c_hi = min(n, c_lo + kResolveChunk);
+    for (size_t o0 = c_lo + (size_t)threadIdx.x * 4; o0 < c_hi; o0 += 256 * 4) {
+        uint32_t d[4];
+        if (o0 + 4 <= n) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(dist + o0);
+            d[0] = q.x;
+            d[1] = q.y;
+            d[2] = q.z;
+            d[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) d[k] = o0 + k < n ? dist[o0 + k] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (d[k]) resolve_one(sb, dist, o0 + k, d[k], work_out, work_count);
+    }
+}
+
+// later rounds: the bytes of the previous round's work list
+__global__ void __launch_bounds__(256) k_resolve(uint8_t *__restrict__ sb, uint32_t *__restrict__ dist, size_t n,
+                                                 const uint32_t *__restrict__ work, uint32_t *__restrict__ work_out,
+                                                 uint32_t *__restrict__ work_count) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t o = work[t];
+    const uint32_t d = dist[o];
+    if (d) resolve_one(sb, dist, o, d, work_out, work_count);
 }
 
 // ============================================================================= K7 un-escape
@@ -509,9 +542,12 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
         size_t todo = (size_t)sbn;
         for (int round = 0; todo; round++) {
             RSN_CUDA(cudaMemsetAsync(count, 0, 4, s));
-            RSN_LAUNCH(k_resolve, (unsigned)div_up(todo, 256), 256, 0, s, sb.as<uint8_t>(), dist.as<uint32_t>(), todo,
-                       round ? wl[(round + 1) & 1].as<uint32_t>() : (const uint32_t *)nullptr, wl[round & 1].as<uint32_t>(),
-                       count);
+            if (round == 0)
+                RSN_LAUNCH(k_resolve4, (unsigned)div_up(todo, kResolveChunk), 256, 0, s, sb.as<uint8_t>(),
+                           dist.as<uint32_t>(), todo, wl[0].as<uint32_t>(), count);
+            else
+                RSN_LAUNCH(k_resolve, (unsigned)div_up(todo, 256), 256, 0, s, sb.as<uint8_t>(), dist.as<uint32_t>(), todo,
+                           wl[(round + 1) & 1].as<uint32_t>(), wl[round & 1].as<uint32_t>(), count);
             RSN_CUDA(cudaMemcpyAsync(c.h_scalars, err.p, 8, cudaMemcpyDeviceToHost, s));
             RSN_CUDA(cudaStreamSynchronize(s));
             const uint32_t e = (uint32_t)c.h_scalars[0];
