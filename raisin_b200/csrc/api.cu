@@ -1,5 +1,6 @@
 // api.cu — the C ABI (include/raisin_b200.h): host-buffer entry points a cgo shim binds,
 // device-buffer entry points, and the engine's layer loops.
+#include "batch.cuh"
 #include "common.cuh"
 #include "huff.cuh"
 #include "lzss.cuh"
@@ -272,6 +273,117 @@ WorkerPool &pool() {
 
 extern "C" {
 
+}  // extern "C"
+
+namespace rsn {
+namespace {
+
+// One stage over a group, file by file (stages without a batched implementation, or groups the
+// batched one declines).
+int stage_per_file(Algo a, bool compress, const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s) {
+    const size_t G = in.size();
+    out.resize(G);
+    out.rc = in.rc;
+    for (size_t f = 0; f < G; f++) {
+        if (in.rc[f] != RSN_OK) continue;
+        uint8_t *next = nullptr;
+        size_t next_n = 0;
+        int rc;
+        if (a == ALGO_LZSS)
+            rc = compress ? lzss_compress_dev(in.ptr[f], in.n[f], 4096, RSN_LZSS_ASYNC, &next, &next_n, s)
+                          : lzss_decompress_dev(in.ptr[f], in.n[f], &next, &next_n, s);
+        else
+            rc = compress ? huff_compress_dev(in.ptr[f], in.n[f], &next, &next_n, s)
+                          : huff_decompress_dev(in.ptr[f], in.n[f], h_in ? h_in[f] : nullptr, 0, &next, &next_n, s);
+        out.rc[f] = rc;
+        if (rc != RSN_OK) continue;
+        out.ptr[f] = next;
+        out.n[f] = next_n;
+        out.owned.push_back(next);
+    }
+    return RSN_OK;
+}
+
+int stage_batched(Algo a, bool compress, const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s) {
+    if (a == ALGO_LZSS && compress) return lzss_compress_batch(in, out, 4096, s);
+    (void)h_in;
+    return RSN_ERR_UNSUPPORTED;
+}
+
+// The files idx[0..G) of a batch through every layer; results to library-owned host buffers.
+int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector<size_t> &idx,
+                const uint8_t *const *in, const size_t *in_n, uint8_t **out, size_t *out_n, int *rcs, cudaStream_t s) {
+    const size_t G = idx.size();
+    ArenaScope scope(s);
+    BatchIO cur;
+    cur.resize(G);
+    size_t total = 0;
+    for (size_t f = 0; f < G; f++) total += (in_n[idx[f]] + 64 + 255) & ~(size_t)255;
+    DevBuf d;
+    RSN_TRY(d.alloc(total + 256, s));
+    std::vector<const uint8_t *> h_in(G);
+    size_t off = 0;
+    for (size_t f = 0; f < G; f++) {
+        const size_t i = idx[f];
+        cur.ptr[f] = d.as<uint8_t>() + off;
+        cur.n[f] = in_n[i];
+        h_in[f] = in[i];
+        if (in_n[i]) RSN_CUDA(cudaMemcpyAsync(d.as<uint8_t>() + off, in[i], in_n[i], cudaMemcpyHostToDevice, s));
+        off += (in_n[i] + 64 + 255) & ~(size_t)255;
+    }
+    const size_t k = algos.size();
+    for (size_t step = 0; step < k; step++) {
+        const Algo a = compress ? algos[step] : algos[k - 1 - step];
+        const uint8_t *const *hp = step == 0 ? h_in.data() : nullptr;  // host copies exist for the first stage only
+        BatchIO next;
+        int rc = stage_batched(a, compress, cur, hp, next, s);
+        if (rc == RSN_ERR_UNSUPPORTED) {
+            next.release(s);
+            rc = stage_per_file(a, compress, cur, hp, next, s);
+        }
+        cur.release(s);
+        if (rc != RSN_OK) {
+            next.release(s);
+            return rc;
+        }
+        cur = std::move(next);
+    }
+    // device -> host: all copies queued, one synchronisation
+    int rc = RSN_OK;
+    for (size_t f = 0; f < G; f++) {
+        const size_t i = idx[f];
+        out[i] = nullptr;
+        out_n[i] = 0;
+        if (rcs) rcs[i] = cur.rc[f];
+        if (cur.rc[f] != RSN_OK) continue;
+        uint8_t *h = (uint8_t *)host_out_alloc(cur.n[f] ? cur.n[f] : 1);
+        if (!h) {
+            if (rcs) rcs[i] = RSN_ERR_NOMEM;
+            rc = RSN_ERR_NOMEM;
+            continue;
+        }
+        if (cur.n[f]) {
+            cudaError_t e = cudaMemcpyAsync(h, cur.ptr[f], cur.n[f], cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "batch d2h", __FILE__, __LINE__);
+        }
+        out[i] = h;
+        out_n[i] = cur.n[f];
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = cuda_fail(e, "batch d2h sync", __FILE__, __LINE__);
+    cur.release(s);
+    return rc;
+}
+
+}  // namespace
+}  // namespace rsn
+
+extern "C" {
+
+// Host buffers (device == 0): small files are cut into groups and every stage runs once per group
+// (batch.cuh); files that are empty or larger than kBatchMaxFile, and device-resident batches
+// (device != 0), go through the per-file path.  Groups and leftover files are spread over
+// `workers` host threads, each with its own stream and arena.
 int rsn_batch_layers(const char *algorithms, int compress, size_t count, const uint8_t *const *in, const size_t *in_n,
                      uint8_t **out, size_t *out_n, int *rcs, int workers, int device) {
     if (!in || !in_n || !out || !out_n) return RSN_ERR_INVALID_ARG;
@@ -280,19 +392,66 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
     RSN_TRY(ensure_ctx());
     const int dev = ctx().device;
     if (workers <= 0) workers = 16;
-    if ((size_t)workers > count) workers = (int)(count ? count : 1);
+    std::vector<int> rc_local;
+    if (!rcs) {
+        rc_local.assign(count ? count : 1, RSN_OK);
+        rcs = rc_local.data();
+    }
+    // groups of small files
+    constexpr size_t kGroupBytes = (size_t)64 << 20, kGroupFiles = 1024;
+    std::vector<std::vector<size_t>> groups;
+    std::vector<size_t> singles;
+    if (!device) {
+        size_t bytes = 0;
+        for (size_t i = 0; i < count; i++) {
+            if (in_n[i] == 0 || in_n[i] > kBatchMaxFile || !in[i]) {
+                singles.push_back(i);
+                continue;
+            }
+            if (groups.empty() || bytes + in_n[i] > kGroupBytes || groups.back().size() >= kGroupFiles) {
+                groups.emplace_back();
+                bytes = 0;
+            }
+            groups.back().push_back(i);
+            bytes += in_n[i];
+        }
+    } else {
+        for (size_t i = 0; i < count; i++) singles.push_back(i);
+    }
+    const size_t units = groups.size() + singles.size();
+    if ((size_t)workers > units) workers = (int)(units ? units : 1);
     std::atomic<size_t> next{0};
     std::atomic<int> first_err{RSN_OK};
+    auto note = [&](int rc) {
+        int expect = RSN_OK;
+        if (rc != RSN_OK) first_err.compare_exchange_strong(expect, rc);
+    };
     auto job = [&]() {
         if (rsn_init(dev) != RSN_OK) {
-            int expect = RSN_OK;
-            first_err.compare_exchange_strong(expect, RSN_ERR_CUDA);
+            note(RSN_ERR_CUDA);
             return;
         }
         cudaStream_t s = ctx().own_stream;
         for (;;) {
-            const size_t i = next.fetch_add(1);
-            if (i >= count) break;
+            const size_t u = next.fetch_add(1);
+            if (u >= units) break;
+            if (u < groups.size()) {
+                const std::vector<size_t> &idx = groups[u];
+                const int rc = batch_group(algos, compress != 0, idx, in, in_n, out, out_n, rcs, s);
+                if (rc != RSN_OK) {  // the whole group failed (device error, out of memory)
+                    for (size_t i : idx) {
+                        if (out[i]) rsn_free(out[i]);
+                        out[i] = nullptr;
+                        out_n[i] = 0;
+                        if (rcs) rcs[i] = rc;
+                    }
+                    note(rc);
+                } else {
+                    for (size_t i : idx) note(rcs[i]);
+                }
+                continue;
+            }
+            const size_t i = singles[u - groups.size()];
             int rc;
             uint8_t *r = nullptr;
             size_t rn = 0;
@@ -319,8 +478,7 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
             if (rc != RSN_OK) {
                 out[i] = nullptr;
                 out_n[i] = 0;
-                int expect = RSN_OK;
-                first_err.compare_exchange_strong(expect, rc);
+                note(rc);
             }
             if (rcs) rcs[i] = rc;
         }

@@ -157,6 +157,8 @@ __device__ __forceinline__ T block_exclusive_sum(T v, T *smem, T &total) {
     return res;
 }
 
+__device__ __forceinline__ size_t div_up_dev(size_t a, size_t b) { return (a + b - 1) / b; }
+
 __device__ __forceinline__ int ndig_u32(uint32_t v) {
     return 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
            (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);

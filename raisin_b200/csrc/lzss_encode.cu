@@ -7,8 +7,11 @@
 //       visits i, i+max(L,1), ...; we rebuild that chain with per-block exit tables composed
 //       through a 64-ary hierarchy, so no pass is sequential in n
 //   K4  token sizing + emit      getEncoding, lzss.go:318-320 and the `<` rule at lzss.go:143
+#include "batch.cuh"
 #include "common.cuh"
 #include "lzss.cuh"
+
+#include <algorithm>
 
 namespace rsn {
 
@@ -17,9 +20,8 @@ namespace rsn {
 __device__ __forceinline__ bool is_special(uint8_t v) { return v == 0x5C || v == 0xFF; }
 
 // tile_cnt[t] = escaped size of tile t; *touched != 0 iff some byte changes ('<', 0x5C or 0xFF)
-__global__ void __launch_bounds__(kTileThreads) k_escape_count(const uint8_t *__restrict__ in, size_t n,
-                                                               uint64_t *__restrict__ tile_cnt,
-                                                               uint32_t *__restrict__ touched) {
+__device__ __forceinline__ void escape_count_body(const uint8_t *__restrict__ in, size_t n,
+                                                  uint64_t *__restrict__ tile_cnt, uint32_t *__restrict__ touched) {
     __shared__ uint32_t sm[33];
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
     uint32_t cnt = 0, changes = 0;
@@ -38,10 +40,14 @@ __global__ void __launch_bounds__(kTileThreads) k_escape_count(const uint8_t *__
     if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
     if (__syncthreads_or(changes != 0) && threadIdx.x == 0) *touched = 1;
 }
+__global__ void __launch_bounds__(kTileThreads) k_escape_count(const uint8_t *__restrict__ in, size_t n,
+                                                               uint64_t *__restrict__ tile_cnt,
+                                                               uint32_t *__restrict__ touched) {
+    escape_count_body(in, n, tile_cnt, touched);
+}
 
-__global__ void __launch_bounds__(kTileThreads) k_escape_apply(const uint8_t *__restrict__ in, size_t n,
-                                                               const uint64_t *__restrict__ tile_off,
-                                                               uint8_t *__restrict__ out) {
+__device__ __forceinline__ void escape_apply_body(const uint8_t *__restrict__ in, size_t n,
+                                                  const uint64_t *__restrict__ tile_off, uint8_t *__restrict__ out) {
     __shared__ uint32_t sm[33];
     __shared__ uint8_t stage[2 * kTile];
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
@@ -71,6 +77,11 @@ __global__ void __launch_bounds__(kTileThreads) k_escape_apply(const uint8_t *__
     __syncthreads();
     uint8_t *dst = out + tile_off[blockIdx.x];
     for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = stage[i];
+}
+__global__ void __launch_bounds__(kTileThreads) k_escape_apply(const uint8_t *__restrict__ in, size_t n,
+                                                               const uint64_t *__restrict__ tile_off,
+                                                               uint8_t *__restrict__ out) {
+    escape_apply_body(in, n, tile_off, out);
 }
 
 // On return *enc_ptr is the escaped buffer: either `enc` (owned) or d_in itself when no byte of
@@ -171,8 +182,8 @@ __device__ __forceinline__ void load_jumps(const ParseCfg &cfg, const uint32_t *
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-__global__ void __launch_bounds__(kPT) k_parse_exits(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
-                                                     uint16_t *__restrict__ E0) {
+__device__ __forceinline__ void parse_exits_body(const ParseCfg &cfg, const uint32_t *__restrict__ lo, size_t n,
+                                                 uint16_t *__restrict__ E0) {
     __shared__ __align__(16) uint16_t y[kPB];
     const size_t start = (size_t)blockIdx.x * kPB;
     const uint32_t nrel = (uint32_t)min((size_t)kPB, n - start);
@@ -222,6 +233,10 @@ __global__ void __launch_bounds__(kPT) k_parse_exits(ParseCfg cfg, const uint32_
             if (p0 + k < nrel) E0[start + p0 + k] = (uint16_t)out[k];
     }
 }
+__global__ void __launch_bounds__(kPT) k_parse_exits(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
+                                                     uint16_t *__restrict__ E0) {
+    parse_exits_body(cfg, lo, n, E0);
+}
 
 struct ParseLevels {
     int top;                 // highest level; level l regions have size kPB * kFan^l
@@ -239,10 +254,9 @@ __device__ __forceinline__ size_t level_step(size_t p, int lvl, size_t rsize, co
 }
 
 // T_l[r][rel] for rel in [0, J]: follow level l-1 until leaving region r (or the input).
-__global__ void k_parse_up(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tprev,
-                           uint16_t *__restrict__ Tcur, int lvl, size_t rsize_prev, size_t rsize_cur, uint32_t J,
-                           size_t n) {
-    const size_t r = blockIdx.y;
+__device__ __forceinline__ void parse_up_body(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tprev,
+                                              uint16_t *__restrict__ Tcur, int lvl, size_t rsize_prev,
+                                              size_t rsize_cur, uint32_t J, size_t n, size_t r) {
     const uint32_t rel = blockIdx.x * blockDim.x + threadIdx.x;
     if (rel > J) return;
     const size_t start = r * rsize_cur, end = start + rsize_cur;
@@ -250,11 +264,16 @@ __global__ void k_parse_up(const uint16_t *__restrict__ E0, const uint16_t *__re
     while (p < end && p < n) p = level_step(p, lvl - 1, rsize_prev, E0, Tprev, J);
     Tcur[r * (size_t)(J + 1) + rel] = (uint16_t)(p >= end ? p - end : 0);
 }
+__global__ void k_parse_up(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tprev,
+                           uint16_t *__restrict__ Tcur, int lvl, size_t rsize_prev, size_t rsize_cur, uint32_t J,
+                           size_t n) {
+    parse_up_body(E0, Tprev, Tcur, lvl, rsize_prev, rsize_cur, J, n, blockIdx.y);
+}
 
 // sequential walk over the (<= kFan) top-level regions
-__global__ void k_parse_top(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Ttop, int lvl,
-                            size_t rsize, size_t regions, uint32_t J, size_t n, uint64_t *__restrict__ entry) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void parse_top_body(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Ttop,
+                                               int lvl, size_t rsize, size_t regions, uint32_t J, size_t n,
+                                               uint64_t *__restrict__ entry) {
     size_t p = 0;
     for (size_t r = 0; r < regions; r++) {
         entry[r] = p;
@@ -262,11 +281,18 @@ __global__ void k_parse_top(const uint16_t *__restrict__ E0, const uint16_t *__r
         if (p < end && p < n) p = level_step(p, lvl, rsize, E0, Ttop, J);
     }
 }
+__global__ void k_parse_top(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Ttop, int lvl,
+                            size_t rsize, size_t regions, uint32_t J, size_t n, uint64_t *__restrict__ entry) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    parse_top_body(E0, Ttop, lvl, rsize, regions, J, n, entry);
+}
 
 // entries of the children (level lvl-1) of each level-lvl region
-__global__ void k_parse_down(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tchild, int child_lvl,
-                             size_t rsize_child, size_t regions_parent, size_t regions_child, uint32_t J, size_t n,
-                             const uint64_t *__restrict__ entry_parent, uint64_t *__restrict__ entry_child) {
+__device__ __forceinline__ void parse_down_body(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tchild,
+                                                int child_lvl, size_t rsize_child, size_t regions_parent,
+                                                size_t regions_child, uint32_t J, size_t n,
+                                                const uint64_t *__restrict__ entry_parent,
+                                                uint64_t *__restrict__ entry_child) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= regions_parent) return;
     size_t p = entry_parent[r];
@@ -277,6 +303,11 @@ __global__ void k_parse_down(const uint16_t *__restrict__ E0, const uint16_t *__
         const size_t end = (cr + 1) * rsize_child;
         if (p < end && p < n) p = level_step(p, child_lvl, rsize_child, E0, Tchild, J);
     }
+}
+__global__ void k_parse_down(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tchild, int child_lvl,
+                             size_t rsize_child, size_t regions_parent, size_t regions_child, uint32_t J, size_t n,
+                             const uint64_t *__restrict__ entry_parent, uint64_t *__restrict__ entry_child) {
+    parse_down_body(E0, Tchild, child_lvl, rsize_child, regions_parent, regions_child, J, n, entry_parent, entry_child);
 }
 
 // ============================================================================= K4 emit
@@ -356,9 +387,9 @@ __device__ __forceinline__ uint8_t *put_dec64(uint8_t *o, uint64_t v) {
 }
 
 // visited bitmap (one u16 per 16 positions) and output bytes of every block
-__global__ void __launch_bounds__(kPT) k_emit_plan(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
-                                                   const uint64_t *__restrict__ entry0,
-                                                   uint16_t *__restrict__ visited, uint64_t *__restrict__ blk_bytes) {
+__device__ __forceinline__ void emit_plan_body(const ParseCfg &cfg, const uint32_t *__restrict__ lo, size_t n,
+                                               const uint64_t *__restrict__ entry0, uint16_t *__restrict__ visited,
+                                               uint64_t *__restrict__ blk_bytes) {
     __shared__ __align__(16) uint16_t ya[kPB], yb[kPB];
     __shared__ __align__(16) uint8_t mark[kPB];
     __shared__ uint32_t sm[33];
@@ -418,13 +449,18 @@ __global__ void __launch_bounds__(kPT) k_emit_plan(ParseCfg cfg, const uint32_t 
     block_exclusive_sum<uint32_t>(bytes, sm, total);
     if (threadIdx.x == 0) blk_bytes[blockIdx.x] = total;
 }
+__global__ void __launch_bounds__(kPT) k_emit_plan(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
+                                                   const uint64_t *__restrict__ entry0,
+                                                   uint16_t *__restrict__ visited, uint64_t *__restrict__ blk_bytes) {
+    emit_plan_body(cfg, lo, n, entry0, visited, blk_bytes);
+}
 
 constexpr int kStage = kPB + 64;  // output bytes of one block never exceed consumed + one token
 
-__global__ void __launch_bounds__(kPT) k_emit_write(ParseCfg cfg, const uint8_t *__restrict__ enc,
-                                                    const uint32_t *__restrict__ lo, size_t n,
-                                                    const uint16_t *__restrict__ visited,
-                                                    const uint64_t *__restrict__ blk_off, uint8_t *__restrict__ out) {
+__device__ __forceinline__ void emit_write_body(const ParseCfg &cfg, const uint8_t *__restrict__ enc,
+                                                const uint32_t *__restrict__ lo, size_t n,
+                                                const uint16_t *__restrict__ visited,
+                                                const uint64_t *__restrict__ blk_off, uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint8_t stage[kStage];
     __shared__ uint32_t sm[33];
     const size_t start = (size_t)blockIdx.x * kPB;
@@ -477,6 +513,12 @@ __global__ void __launch_bounds__(kPT) k_emit_write(ParseCfg cfg, const uint8_t 
         *reinterpret_cast<uint4 *>(dst + head + v * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
     for (uint32_t i = head + nvec * 16 + threadIdx.x; i < total; i += blockDim.x) dst[i] = stage[i];
+}
+__global__ void __launch_bounds__(kPT) k_emit_write(ParseCfg cfg, const uint8_t *__restrict__ enc,
+                                                    const uint32_t *__restrict__ lo, size_t n,
+                                                    const uint16_t *__restrict__ visited,
+                                                    const uint64_t *__restrict__ blk_off, uint8_t *__restrict__ out) {
+    emit_write_body(cfg, enc, lo, n, visited, blk_off, out);
 }
 
 // ============================================================================= variant B: start bits
@@ -661,6 +703,239 @@ int lzss_compress_dev_ex(const uint8_t *d_in, size_t n, int64_t window, int vari
         cfg.sbits = sbits.as<uint32_t>();
     }
     return parse_and_emit(enc, en, cfg, packed, d_out, out_n, s);
+}
+
+// ============================================================================= batches of small files
+//
+// The same kernels, one launch per stage for a whole group of files (batch.cuh).  File sizes after
+// escaping live in the LzFile records on the device; grids are sized for the largest possible file
+// and CTAs beyond a file's real size leave at once.
+
+struct LzBatch {
+    LzFile *files;
+    uint32_t window;
+    uint64_t *tile_cnt, *tile_off;  // [G][tc_stride]
+    size_t tc_stride;
+    uint8_t *enc;                   // [G][enc_stride]
+    size_t enc_stride;
+    uint32_t *packed;               // [G][packed_stride]
+    size_t packed_stride;
+    uint16_t *E0;                   // [G][e0_stride]
+    size_t e0_stride;
+    uint16_t *T1;                   // [G][t1_stride]   level-1 exit tables (top == 1 only)
+    size_t t1_stride;
+    uint64_t *entry0, *entry1;      // [G][entry0_stride], [G][entry1_stride]
+    size_t entry0_stride, entry1_stride;
+    uint16_t *vis;                  // [G][vis_stride]
+    size_t vis_stride;
+    uint64_t *bb, *bo;              // [G][bb_stride]
+    size_t bb_stride;
+    uint64_t *out_n;                // [G]
+    int top;                        // 0: one level of blocks; 1: blocks grouped kFan at a time
+};
+
+__device__ __forceinline__ ParseCfg batch_cfg(const LzFile &f) {
+    return ParseCfg{f.W, f.W, RSN_LZSS_ASYNC, nullptr};
+}
+
+__global__ void __launch_bounds__(kTileThreads) kb_escape_count(LzBatch b) {
+    LzFile &f = b.files[blockIdx.y];
+    if ((size_t)blockIdx.x * kTile >= f.n) return;
+    escape_count_body(f.in, (size_t)f.n, b.tile_cnt + (size_t)blockIdx.y * b.tc_stride, &f.touched);
+}
+
+// per file: tile offsets, escaped size, effective window (lzss.go:125: the window never exceeds the data)
+__global__ void __launch_bounds__(256) kb_escape_finish(LzBatch b) {
+    __shared__ uint64_t sm[33];
+    LzFile &f = b.files[blockIdx.x];
+    const size_t tiles = div_up_dev((size_t)f.n, (size_t)kTile);
+    const uint64_t total = cta_scan_u64(b.tile_cnt + (size_t)blockIdx.x * b.tc_stride,
+                                        b.tile_off + (size_t)blockIdx.x * b.tc_stride, tiles, sm);
+    if (threadIdx.x == 0) {
+        const bool alias = f.touched == 0 && (reinterpret_cast<uintptr_t>(f.in) & 15) == 0;
+        f.enc = alias ? f.in : b.enc + (size_t)blockIdx.x * b.enc_stride;
+        f.touched = alias ? 0u : 1u;
+        f.en = total;
+        uint64_t w = b.window;
+        if (w > total) w = total;
+        if (w < 1) w = 1;
+        f.W = (uint32_t)w;
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads) kb_escape_apply(LzBatch b) {
+    const LzFile &f = b.files[blockIdx.y];
+    if (!f.touched || (size_t)blockIdx.x * kTile >= f.n) return;
+    escape_apply_body(f.in, (size_t)f.n, b.tile_off + (size_t)blockIdx.y * b.tc_stride, const_cast<uint8_t *>(f.enc));
+}
+
+__global__ void __launch_bounds__(kPT) kb_parse_exits(LzBatch b) {
+    const LzFile &f = b.files[blockIdx.y];
+    if ((size_t)blockIdx.x * kPB >= f.en) return;
+    parse_exits_body(batch_cfg(f), b.packed + (size_t)blockIdx.y * b.packed_stride, (size_t)f.en,
+                     b.E0 + (size_t)blockIdx.y * b.e0_stride);
+}
+
+__global__ void kb_parse_up(LzBatch b) {  // grid: (rel chunks, level-1 regions, files)
+    const LzFile &f = b.files[blockIdx.z];
+    const size_t rsize1 = (size_t)kPB * kFan;
+    if ((size_t)blockIdx.y * rsize1 >= f.en) return;
+    parse_up_body(b.E0 + (size_t)blockIdx.z * b.e0_stride, nullptr, b.T1 + (size_t)blockIdx.z * b.t1_stride, 1, kPB,
+                  rsize1, f.W, (size_t)f.en, blockIdx.y);
+}
+
+__global__ void kb_parse_top(LzBatch b, size_t G) {  // one thread per file
+    const size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= G) return;
+    const LzFile &f = b.files[y];
+    if (f.en == 0) return;
+    const size_t rsize = b.top ? (size_t)kPB * kFan : (size_t)kPB;
+    uint64_t *entry = b.top ? b.entry1 + y * b.entry1_stride : b.entry0 + y * b.entry0_stride;
+    parse_top_body(b.E0 + y * b.e0_stride, b.top ? b.T1 + y * b.t1_stride : nullptr, b.top, rsize,
+                   div_up_dev((size_t)f.en, rsize), f.W, (size_t)f.en, entry);
+}
+
+__global__ void kb_parse_down(LzBatch b) {  // top == 1: level-1 regions -> blocks
+    const LzFile &f = b.files[blockIdx.y];
+    if (f.en == 0) return;
+    parse_down_body(b.E0 + (size_t)blockIdx.y * b.e0_stride, nullptr, 0, kPB,
+                    div_up_dev((size_t)f.en, (size_t)kPB * kFan), div_up_dev((size_t)f.en, (size_t)kPB), f.W,
+                    (size_t)f.en, b.entry1 + (size_t)blockIdx.y * b.entry1_stride,
+                    b.entry0 + (size_t)blockIdx.y * b.entry0_stride);
+}
+
+__global__ void __launch_bounds__(kPT) kb_emit_plan(LzBatch b) {
+    const LzFile &f = b.files[blockIdx.y];
+    if ((size_t)blockIdx.x * kPB >= f.en) return;
+    emit_plan_body(batch_cfg(f), b.packed + (size_t)blockIdx.y * b.packed_stride, (size_t)f.en,
+                   b.entry0 + (size_t)blockIdx.y * b.entry0_stride, b.vis + (size_t)blockIdx.y * b.vis_stride,
+                   b.bb + (size_t)blockIdx.y * b.bb_stride);
+}
+
+__global__ void __launch_bounds__(256) kb_emit_finish(LzBatch b) {
+    __shared__ uint64_t sm[33];
+    LzFile &f = b.files[blockIdx.x];
+    const size_t blocks = div_up_dev((size_t)f.en, (size_t)kPB);
+    const uint64_t total = cta_scan_u64(b.bb + (size_t)blockIdx.x * b.bb_stride, b.bo + (size_t)blockIdx.x * b.bb_stride,
+                                        blocks, sm);
+    if (threadIdx.x == 0) {
+        f.out_n = total;
+        b.out_n[blockIdx.x] = total;
+    }
+}
+
+__global__ void __launch_bounds__(kPT) kb_emit_write(LzBatch b, uint8_t *const *__restrict__ outp) {
+    const LzFile &f = b.files[blockIdx.y];
+    if ((size_t)blockIdx.x * kPB >= f.en) return;
+    emit_write_body(batch_cfg(f), f.enc, b.packed + (size_t)blockIdx.y * b.packed_stride, (size_t)f.en,
+                    b.vis + (size_t)blockIdx.y * b.vis_stride, b.bo + (size_t)blockIdx.y * b.bb_stride,
+                    outp[blockIdx.y]);
+}
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// lz.CompressAsync (lzss.go:109-154) over every file of the group; window in [1, 4096].
+int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStream_t s) {
+    const size_t G = in.size();
+    out.resize(G);
+    out.rc = in.rc;
+    if (G == 0) return RSN_OK;
+    if (window < 1 || window > 4096) return RSN_ERR_UNSUPPORTED;
+    ArenaScope scope(s);
+    Ctx &c = ctx();
+    size_t cap = 1;
+    for (size_t f = 0; f < G; f++)
+        if (in.rc[f] == RSN_OK) cap = std::max<size_t>(cap, in.n[f]);
+    if (cap > kBatchMaxFile) return RSN_ERR_UNSUPPORTED;
+    const size_t ecap = round_up(2 * cap, 8192);  // escaping at most doubles a file
+    const size_t tiles_cap = div_up(cap, kTile), blocks_cap = ecap / kPB;
+    LzBatch b{};
+    b.window = (uint32_t)window;
+    b.top = blocks_cap > (size_t)kFan ? 1 : 0;
+    const size_t regions1 = div_up(blocks_cap, kFan);
+    if (regions1 > (size_t)kFan) return RSN_ERR_UNSUPPORTED;
+    b.tc_stride = tiles_cap + 1;
+    b.enc_stride = ecap + 256;
+    b.packed_stride = ecap + 64;
+    b.e0_stride = ecap + 64;
+    b.t1_stride = regions1 * ((size_t)window + 1);
+    b.entry0_stride = blocks_cap;
+    b.entry1_stride = regions1;
+    b.vis_stride = blocks_cap * (kPB / 16);
+    b.bb_stride = blocks_cap + 1;
+
+    std::vector<LzFile> h_files(G);
+    for (size_t f = 0; f < G; f++) {
+        LzFile r{};
+        r.in = in.ptr[f];
+        r.n = in.rc[f] == RSN_OK ? in.n[f] : 0;
+        h_files[f] = r;
+    }
+    DevBuf files, tcnt, toff, enc, packed, E0, T1, e0, e1, vis, bb, bo, outn, outp;
+    RSN_TRY(files.alloc(G * sizeof(LzFile), s));
+    RSN_TRY(tcnt.alloc(G * b.tc_stride * 8, s));
+    RSN_TRY(toff.alloc(G * b.tc_stride * 8, s));
+    RSN_TRY(enc.alloc(G * b.enc_stride, s));
+    RSN_TRY(packed.alloc(G * b.packed_stride * 4, s));
+    RSN_TRY(E0.alloc(G * b.e0_stride * 2, s));
+    if (b.top) RSN_TRY(T1.alloc(G * b.t1_stride * 2, s));
+    RSN_TRY(e0.alloc(G * b.entry0_stride * 8, s));
+    RSN_TRY(e1.alloc(G * b.entry1_stride * 8, s));
+    RSN_TRY(vis.alloc(G * b.vis_stride * 2, s));
+    RSN_TRY(bb.alloc(G * b.bb_stride * 8, s));
+    RSN_TRY(bo.alloc(G * b.bb_stride * 8, s));
+    RSN_TRY(outn.alloc(G * 8, s));
+    RSN_TRY(outp.alloc(G * 8, s));
+    b.files = files.as<LzFile>();
+    b.tile_cnt = tcnt.as<uint64_t>();
+    b.tile_off = toff.as<uint64_t>();
+    b.enc = enc.as<uint8_t>();
+    b.packed = packed.as<uint32_t>();
+    b.E0 = E0.as<uint16_t>();
+    b.T1 = T1.as<uint16_t>();
+    b.entry0 = e0.as<uint64_t>();
+    b.entry1 = e1.as<uint64_t>();
+    b.vis = vis.as<uint16_t>();
+    b.bb = bb.as<uint64_t>();
+    b.bo = bo.as<uint64_t>();
+    b.out_n = outn.as<uint64_t>();
+    RSN_CUDA(cudaMemcpyAsync(files.p, h_files.data(), G * sizeof(LzFile), cudaMemcpyHostToDevice, s));
+
+    const unsigned g = (unsigned)G;
+    RSN_LAUNCH(kb_escape_count, dim3((unsigned)tiles_cap, g), kTileThreads, 0, s, b);
+    RSN_LAUNCH(kb_escape_finish, g, 256, 0, s, b);
+    RSN_LAUNCH(kb_escape_apply, dim3((unsigned)tiles_cap, g), kTileThreads, 0, s, b);
+    RSN_TRY(lzss_match_tile_batch(b.files, G, ecap, b.window, b.packed, b.packed_stride, s));
+    RSN_LAUNCH(kb_parse_exits, dim3((unsigned)blocks_cap, g), kPT, 0, s, b);
+    if (b.top)
+        RSN_LAUNCH(kb_parse_up, dim3((unsigned)div_up((size_t)window + 1, 256), (unsigned)regions1, g), 256, 0, s, b);
+    RSN_LAUNCH(kb_parse_top, (unsigned)div_up(G, 64), 64, 0, s, b, G);
+    if (b.top) RSN_LAUNCH(kb_parse_down, dim3((unsigned)div_up(regions1, 128), g), 128, 0, s, b);
+    RSN_LAUNCH(kb_emit_plan, dim3((unsigned)blocks_cap, g), kPT, 0, s, b);
+    RSN_LAUNCH(kb_emit_finish, g, 256, 0, s, b);
+    std::vector<uint64_t> h_outn(G);
+    RSN_CUDA(cudaMemcpyAsync(h_outn.data(), outn.p, G * 8, cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+
+    // one result buffer for the group, files at 256-byte aligned offsets
+    std::vector<uint8_t *> h_outp(G);
+    size_t total = 0;
+    for (size_t f = 0; f < G; f++) total += round_up(h_outn[f] + 16, 256);
+    DevBuf res;
+    RSN_TRY(res.alloc_out(total + 256, s));
+    size_t off = 0;
+    for (size_t f = 0; f < G; f++) {
+        h_outp[f] = res.as<uint8_t>() + off;
+        out.ptr[f] = h_outp[f];
+        out.n[f] = h_outn[f];
+        off += round_up(h_outn[f] + 16, 256);
+    }
+    RSN_CUDA(cudaMemcpyAsync(outp.p, h_outp.data(), G * 8, cudaMemcpyHostToDevice, s));
+    RSN_LAUNCH(kb_emit_write, dim3((unsigned)blocks_cap, g), kPT, 0, s, b, outp.as<uint8_t *>());
+    RSN_CUDA(cudaStreamSynchronize(s));  // h_outp is read by the copy above
+    out.owned.push_back(res.release());
+    (void)c;
+    return RSN_OK;
 }
 
 }  // namespace rsn

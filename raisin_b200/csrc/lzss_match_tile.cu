@@ -191,8 +191,8 @@ __device__ __forceinline__ void slot_range(const Smem &sm, const uint16_t *arr, 
 
 }  // namespace tile
 
-__global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
-                                                              uint32_t *__restrict__ packed, size_t first_tile) {
+__device__ __forceinline__ void match_tile_body(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
+                                                uint32_t *__restrict__ packed, size_t first_tile) {
     using namespace tile;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -427,11 +427,22 @@ __global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__r
         if (v != 0xFF) packed[tile_start + x] = (uint32_t)v << 16;
     }
 }
+__global__ void __launch_bounds__(tile::THREADS) k_match_tile(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
+                                                              uint32_t *__restrict__ packed, size_t first_tile) {
+    match_tile_body(enc, n, W, packed, first_tile);
+}
+// one tile of one file of a batch (blockIdx.y = file)
+__global__ void __launch_bounds__(tile::THREADS) kb_match_tile(const LzFile *__restrict__ files,
+                                                               uint32_t *__restrict__ packed, size_t packed_stride) {
+    const LzFile &f = files[blockIdx.y];
+    if ((size_t)blockIdx.x * tile::T >= f.en) return;
+    match_tile_body(f.enc, (size_t)f.en, f.W, packed + (size_t)blockIdx.y * packed_stride, 0);
+}
 
 // Tile 0 has no halo, so stream positions 0 and 1 never appear as the third byte of an entry and
 // position 0 never as the second: add the 1- and 2-byte matches whose source starts there.
-__global__ void k_match_tile_fix0(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
-                                  uint32_t *__restrict__ packed) {
+__device__ __forceinline__ void match_tile_fix0_body(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
+                                                     uint32_t *__restrict__ packed) {
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n || q > (size_t)W + 1) return;
     uint32_t L = packed[q] >> 16;
@@ -443,6 +454,15 @@ __global__ void k_match_tile_fix0(const uint8_t *__restrict__ enc, size_t n, uin
     if (q >= 1 && q <= W && enc[0] == enc[q]) want = max(want, 1u);
     if (q >= 2 && q - 1 <= W && enc[1] == enc[q]) want = max(want, 1u);
     if (want != L) packed[q] = want << 16;
+}
+__global__ void k_match_tile_fix0(const uint8_t *__restrict__ enc, size_t n, uint32_t W,
+                                  uint32_t *__restrict__ packed) {
+    match_tile_fix0_body(enc, n, W, packed);
+}
+__global__ void kb_match_tile_fix0(const LzFile *__restrict__ files, uint32_t *__restrict__ packed,
+                                   size_t packed_stride) {
+    const LzFile &f = files[blockIdx.y];
+    match_tile_fix0_body(f.enc, (size_t)f.en, f.W, packed + (size_t)blockIdx.y * packed_stride);
 }
 
 int lzss_match_tile(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, cudaStream_t s) {
@@ -474,5 +494,21 @@ int lzss_match_tile_range(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *
     return RSN_OK;
 }
 size_t lzss_match_tile_size() { return tile::T; }
+
+// every file of a batch: files[f].enc / en / W are device-resident (en <= ecap, W <= window <= 4096)
+int lzss_match_tile_batch(const LzFile *d_files, size_t G, size_t ecap, uint32_t window, uint32_t *d_packed,
+                          size_t packed_stride, cudaStream_t s) {
+    static thread_local bool attr_set = false;
+    const size_t smem = sizeof(tile::Smem);
+    if (!attr_set) {
+        RSN_CUDA(cudaFuncSetAttribute(kb_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const dim3 grid((unsigned)div_up(ecap, tile::T), (unsigned)G);
+    RSN_LAUNCH(kb_match_tile, grid, tile::THREADS, smem, s, d_files, d_packed, packed_stride);
+    const dim3 gfix((unsigned)div_up((size_t)window + 2, 128), (unsigned)G);
+    RSN_LAUNCH(kb_match_tile_fix0, gfix, 128, 0, s, d_files, d_packed, packed_stride);
+    return RSN_OK;
+}
 
 }  // namespace rsn
