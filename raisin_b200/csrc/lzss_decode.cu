@@ -10,8 +10,12 @@
 //   K5c  scatter literals and per-byte source distances
 //   K6   back-reference resolve by bounded pointer chasing with path compression
 //   K7   un-escape: a 2-state transducer, same scan pattern, compacting
+#include "batch.cuh"
 #include "common.cuh"
 #include "lzss.cuh"
+
+#include <algorithm>
+#include <vector>
 
 namespace rsn {
 
@@ -61,8 +65,8 @@ __device__ __forceinline__ uint8_t thread_map(const uint8_t (&v)[16], int valid)
     return m;
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_tok_reduce(const uint8_t *__restrict__ in, size_t n,
-                                                             uint8_t *__restrict__ tile_map) {
+__device__ __forceinline__ void tok_reduce_body(const uint8_t *__restrict__ in, size_t n,
+                                                uint8_t *__restrict__ tile_map) {
     __shared__ uint8_t buf[kTileThreads];
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
     uint8_t m = kMapId;
@@ -74,10 +78,14 @@ __global__ void __launch_bounds__(kTileThreads) k_tok_reduce(const uint8_t *__re
     m = block_inclusive_scan_generic<uint8_t>(m, buf, MapCompose());
     if (threadIdx.x == blockDim.x - 1) tile_map[blockIdx.x] = m;
 }
+__global__ void __launch_bounds__(kTileThreads) k_tok_reduce(const uint8_t *__restrict__ in, size_t n,
+                                                             uint8_t *__restrict__ tile_map) {
+    tok_reduce_body(in, n, tile_map);
+}
 
 // state in front of each tile, starting from Open
-__global__ void __launch_bounds__(1024) k_tok_spine(const uint8_t *__restrict__ tile_map, size_t tiles,
-                                                    uint8_t *__restrict__ tile_state) {
+__device__ __forceinline__ void tok_spine_body(const uint8_t *__restrict__ tile_map, size_t tiles,
+                                               uint8_t *__restrict__ tile_state) {
     __shared__ uint8_t buf[1024];
     uint8_t carry = ST_OPEN;
     for (size_t base = 0; base < tiles; base += blockDim.x) {
@@ -92,6 +100,10 @@ __global__ void __launch_bounds__(1024) k_tok_spine(const uint8_t *__restrict__ 
         carry = map_apply(last, carry);
         (void)inc;
     }
+}
+__global__ void __launch_bounds__(1024) k_tok_spine(const uint8_t *__restrict__ tile_map, size_t tiles,
+                                                    uint8_t *__restrict__ tile_state) {
+    tok_spine_body(tile_map, tiles, tile_state);
 }
 
 // ============================================================================= K5b/K5c tokens
@@ -172,11 +184,11 @@ constexpr int kMaxTok = kTile / 3 + 2;  // "<,>" is the shortest token
 // one lane at a time).  WRITE == false: output bytes of the tile.  WRITE == true: literals to
 // sb, pointer distances of referenced bytes to dist (zero-filled beforehand).
 template <bool WRITE>
-__global__ void __launch_bounds__(kTileThreads) k_tok_tile(const uint8_t *__restrict__ in, size_t n,
-                                                           const uint8_t *__restrict__ tile_state,
-                                                           const uint64_t *__restrict__ tile_off,
-                                                           uint64_t *__restrict__ tile_out, uint8_t *__restrict__ sb,
-                                                           uint32_t *__restrict__ dist, uint32_t *__restrict__ err) {
+__device__ __forceinline__ void tok_tile_body(const uint8_t *__restrict__ in, size_t n,
+                                              const uint8_t *__restrict__ tile_state,
+                                              const uint64_t *__restrict__ tile_off, uint64_t *__restrict__ tile_out,
+                                              uint8_t *__restrict__ sb, uint32_t *__restrict__ dist,
+                                              uint32_t *__restrict__ err) {
     __shared__ uint8_t buf[kTileThreads];
     __shared__ uint64_t sm64[33];
     __shared__ uint32_t sm32[33];
@@ -280,6 +292,14 @@ __global__ void __launch_bounds__(kTileThreads) k_tok_tile(const uint8_t *__rest
         if (ptr > off) continue;
         for (uint64_t q = threadIdx.x; q < cnt; q += blockDim.x) dist[off + q] = (uint32_t)ptr;
     }
+}
+template <bool WRITE>
+__global__ void __launch_bounds__(kTileThreads) k_tok_tile(const uint8_t *__restrict__ in, size_t n,
+                                                           const uint8_t *__restrict__ tile_state,
+                                                           const uint64_t *__restrict__ tile_off,
+                                                           uint64_t *__restrict__ tile_out, uint8_t *__restrict__ sb,
+                                                           uint32_t *__restrict__ dist, uint32_t *__restrict__ err) {
+    tok_tile_body<WRITE>(in, n, tile_state, tile_off, tile_out, sb, dist, err);
 }
 
 // ============================================================================= K6 resolve
@@ -391,8 +411,8 @@ __device__ __forceinline__ UnescAgg unesc_thread(const uint8_t (&v)[16], int val
     return r;
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_unesc_reduce(const uint8_t *__restrict__ in, size_t n,
-                                                               UnescAgg *__restrict__ tile_agg) {
+__device__ __forceinline__ void unesc_reduce_body(const uint8_t *__restrict__ in, size_t n,
+                                                  UnescAgg *__restrict__ tile_agg) {
     __shared__ UnescAgg buf[kTileThreads];
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
     UnescAgg a = unesc_identity();
@@ -404,11 +424,15 @@ __global__ void __launch_bounds__(kTileThreads) k_unesc_reduce(const uint8_t *__
     a = block_inclusive_scan_generic<UnescAgg>(a, buf, UnescCompose());
     if (threadIdx.x == blockDim.x - 1) tile_agg[blockIdx.x] = a;
 }
+__global__ void __launch_bounds__(kTileThreads) k_unesc_reduce(const uint8_t *__restrict__ in, size_t n,
+                                                               UnescAgg *__restrict__ tile_agg) {
+    unesc_reduce_body(in, n, tile_agg);
+}
 
 // per tile: incoming escape state and output offset; total output size
-__global__ void __launch_bounds__(1024) k_unesc_spine(const UnescAgg *__restrict__ tile_agg, size_t tiles,
-                                                      uint8_t *__restrict__ tile_state,
-                                                      uint64_t *__restrict__ tile_off, uint64_t *__restrict__ total) {
+__device__ __forceinline__ void unesc_spine_body(const UnescAgg *__restrict__ tile_agg, size_t tiles,
+                                                 uint8_t *__restrict__ tile_state, uint64_t *__restrict__ tile_off,
+                                                 uint64_t *__restrict__ total) {
     __shared__ UnescAgg buf[1024];
     uint32_t carry_state = 0;
     uint64_t carry_off = 0;
@@ -428,11 +452,15 @@ __global__ void __launch_bounds__(1024) k_unesc_spine(const UnescAgg *__restrict
     }
     if (threadIdx.x == 0) *total = carry_off;
 }
+__global__ void __launch_bounds__(1024) k_unesc_spine(const UnescAgg *__restrict__ tile_agg, size_t tiles,
+                                                      uint8_t *__restrict__ tile_state,
+                                                      uint64_t *__restrict__ tile_off, uint64_t *__restrict__ total) {
+    unesc_spine_body(tile_agg, tiles, tile_state, tile_off, total);
+}
 
-__global__ void __launch_bounds__(kTileThreads) k_unesc_apply(const uint8_t *__restrict__ in, size_t n,
-                                                              const uint8_t *__restrict__ tile_state,
-                                                              const uint64_t *__restrict__ tile_off,
-                                                              uint8_t *__restrict__ out) {
+__device__ __forceinline__ void unesc_apply_body(const uint8_t *__restrict__ in, size_t n,
+                                                 const uint8_t *__restrict__ tile_state,
+                                                 const uint64_t *__restrict__ tile_off, uint8_t *__restrict__ out) {
     __shared__ UnescAgg buf[kTileThreads];
     __shared__ uint8_t stage[kTile];
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
@@ -467,6 +495,12 @@ __global__ void __launch_bounds__(kTileThreads) k_unesc_apply(const uint8_t *__r
     __syncthreads();
     uint8_t *dst = out + tile_off[blockIdx.x];
     for (uint32_t i = threadIdx.x; i < tile_total; i += blockDim.x) dst[i] = stage[i];
+}
+__global__ void __launch_bounds__(kTileThreads) k_unesc_apply(const uint8_t *__restrict__ in, size_t n,
+                                                              const uint8_t *__restrict__ tile_state,
+                                                              const uint64_t *__restrict__ tile_off,
+                                                              uint8_t *__restrict__ out) {
+    unesc_apply_body(in, n, tile_state, tile_off, out);
 }
 
 static int lzss_unescape(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s) {
@@ -564,6 +598,207 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
     const int rc = lzss_unescape(sb.as<uint8_t>(), (size_t)sbn, d_out, out_n, s);
     tr.mark("unescape");
     return rc;
+}
+
+// ============================================================================= batches of small files
+//
+// One launch per kernel for a whole group of files (batch.cuh).  The decoded files of a group sit
+// back to back in ONE buffer, with one distance array beside it: a validated pointer never reaches
+// below the start of its own file, so the resolve kernels run over the whole buffer as if it were
+// a single stream, and only the token kernels know about files.
+
+struct DecFile {
+    const uint8_t *in;
+    uint64_t n;        // 0: not part of this phase
+    uint64_t gbase;    // offset of the file's bytes in the group buffers (phase B on)
+    uint64_t sbn;      // decoded size before un-escaping
+    uint64_t un_n;     // size after un-escaping
+    uint32_t flags;    // ERR_BAD_REF | FLAG_NEEDS_UNESCAPE
+    uint32_t unesc;    // phase C runs on this file
+};
+
+struct DecBatch {
+    DecFile *files;
+    uint8_t *tmap, *tstate;       // [G][tc_stride]
+    uint64_t *tout, *toff;        // [G][tc_stride]
+    size_t tc_stride;
+    uint8_t *sb, *out2;           // group buffers
+    uint32_t *dist;
+    UnescAgg *agg;                // [G][uc_stride]
+    uint8_t *ustate;
+    uint64_t *uoff;
+    size_t uc_stride;
+};
+
+__global__ void __launch_bounds__(kTileThreads) kb_tok_reduce(DecBatch b) {
+    const DecFile &f = b.files[blockIdx.y];
+    if ((size_t)blockIdx.x * kTile >= f.n) return;
+    tok_reduce_body(f.in, (size_t)f.n, b.tmap + (size_t)blockIdx.y * b.tc_stride);
+}
+__global__ void __launch_bounds__(1024) kb_tok_spine(DecBatch b) {
+    const DecFile &f = b.files[blockIdx.x];
+    if (f.n == 0) return;
+    tok_spine_body(b.tmap + (size_t)blockIdx.x * b.tc_stride, div_up_dev((size_t)f.n, (size_t)kTile),
+                   b.tstate + (size_t)blockIdx.x * b.tc_stride);
+}
+template <bool WRITE>
+__global__ void __launch_bounds__(kTileThreads) kb_tok_tile(DecBatch b) {
+    DecFile &f = b.files[blockIdx.y];
+    if ((size_t)blockIdx.x * kTile >= f.n) return;
+    const size_t o = (size_t)blockIdx.y * b.tc_stride;
+    tok_tile_body<WRITE>(f.in, (size_t)f.n, b.tstate + o, b.toff + o, b.tout + o, WRITE ? b.sb + f.gbase : nullptr,
+                         WRITE ? b.dist + f.gbase : nullptr, &f.flags);
+}
+__global__ void __launch_bounds__(256) kb_tok_finish(DecBatch b) {
+    __shared__ uint64_t sm[33];
+    DecFile &f = b.files[blockIdx.x];
+    const size_t o = (size_t)blockIdx.x * b.tc_stride;
+    const uint64_t total = cta_scan_u64(b.tout + o, b.toff + o, div_up_dev((size_t)f.n, (size_t)kTile), sm);
+    if (threadIdx.x == 0) f.sbn = total;
+}
+
+__global__ void __launch_bounds__(kTileThreads) kb_unesc_reduce(DecBatch b) {
+    const DecFile &f = b.files[blockIdx.y];
+    if (!f.unesc || (size_t)blockIdx.x * kTile >= f.sbn) return;
+    unesc_reduce_body(b.sb + f.gbase, (size_t)f.sbn, b.agg + (size_t)blockIdx.y * b.uc_stride);
+}
+__global__ void __launch_bounds__(1024) kb_unesc_spine(DecBatch b) {
+    DecFile &f = b.files[blockIdx.x];
+    if (!f.unesc) return;
+    const size_t o = (size_t)blockIdx.x * b.uc_stride;
+    unesc_spine_body(b.agg + o, div_up_dev((size_t)f.sbn, (size_t)kTile), b.ustate + o, b.uoff + o, &f.un_n);
+}
+__global__ void __launch_bounds__(kTileThreads) kb_unesc_apply(DecBatch b) {
+    const DecFile &f = b.files[blockIdx.y];
+    if (!f.unesc || (size_t)blockIdx.x * kTile >= f.sbn) return;
+    const size_t o = (size_t)blockIdx.y * b.uc_stride;
+    unesc_apply_body(b.sb + f.gbase, (size_t)f.sbn, b.ustate + o, b.uoff + o, b.out2 + f.gbase);
+}
+
+// lz.Decompress (lzss.go:323-364 + 391-406) over every file of the group.
+int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
+    const size_t G = in.size();
+    out.resize(G);
+    out.rc = in.rc;
+    if (G == 0) return RSN_OK;
+    ArenaScope scope(s);
+    size_t cap = 1;
+    for (size_t f = 0; f < G; f++)
+        if (in.rc[f] == RSN_OK) cap = std::max<size_t>(cap, in.n[f]);
+    if (cap > kBatchMaxFile) return RSN_ERR_UNSUPPORTED;
+    const size_t tiles_cap = div_up(cap, kTile);
+    DecBatch b{};
+    b.tc_stride = tiles_cap + 1;
+    std::vector<DecFile> h(G);
+    for (size_t f = 0; f < G; f++) {
+        h[f] = DecFile{};
+        h[f].in = in.ptr[f];
+        h[f].n = in.rc[f] == RSN_OK ? in.n[f] : 0;
+    }
+    DevBuf files, tmap, tstate, tout, toff;
+    RSN_TRY(files.alloc(G * sizeof(DecFile), s));
+    RSN_TRY(tmap.alloc(G * b.tc_stride, s));
+    RSN_TRY(tstate.alloc(G * b.tc_stride, s));
+    RSN_TRY(tout.alloc(G * b.tc_stride * 8, s));
+    RSN_TRY(toff.alloc(G * b.tc_stride * 8, s));
+    b.files = files.as<DecFile>();
+    b.tmap = tmap.as<uint8_t>();
+    b.tstate = tstate.as<uint8_t>();
+    b.tout = tout.as<uint64_t>();
+    b.toff = toff.as<uint64_t>();
+    const unsigned g = (unsigned)G;
+    const dim3 tgrid((unsigned)tiles_cap, g);
+    // ---- phase A: token states and decoded sizes
+    RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(DecFile), cudaMemcpyHostToDevice, s));
+    RSN_LAUNCH(kb_tok_reduce, tgrid, kTileThreads, 0, s, b);
+    RSN_LAUNCH(kb_tok_spine, g, 1024, 0, s, b);
+    RSN_LAUNCH(kb_tok_tile<false>, tgrid, kTileThreads, 0, s, b);
+    RSN_LAUNCH(kb_tok_finish, g, 256, 0, s, b);
+    RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(DecFile), cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    size_t total = 0, sb_cap = 1;
+    for (size_t f = 0; f < G; f++) {
+        if (h[f].n && (h[f].flags & ERR_BAD_REF)) {
+            out.rc[f] = RSN_ERR_BAD_REFERENCE;
+            h[f].n = 0;
+        }
+        if (out.rc[f] != RSN_OK) {
+            h[f].n = 0;
+            h[f].sbn = 0;
+        }
+        h[f].gbase = total;
+        total += (h[f].sbn + 16 + 255) & ~(uint64_t)255;
+        sb_cap = std::max<size_t>(sb_cap, h[f].sbn);
+    }
+    if (total > ((size_t)1 << 30)) return RSN_ERR_UNSUPPORTED;  // the per-file path takes such groups
+    // ---- phase B: literals and distances, then the chase
+    DevBuf sb, dist, wl[2], cnt;
+    RSN_TRY(sb.alloc_out(total + 256, s));
+    RSN_TRY(dist.alloc(total * 4 + 64, s));
+    RSN_TRY(cnt.alloc(16, s));
+    RSN_CUDA(cudaMemsetAsync(dist.p, 0, total * 4 + 64, s));
+    b.sb = sb.as<uint8_t>();
+    b.dist = dist.as<uint32_t>();
+    RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(DecFile), cudaMemcpyHostToDevice, s));
+    RSN_LAUNCH(kb_tok_tile<true>, tgrid, kTileThreads, 0, s, b);
+    RSN_TRY(wl[0].alloc(total * 4 + 16, s));
+    RSN_TRY(wl[1].alloc(total * 4 + 16, s));
+    Ctx &c = ctx();
+    size_t todo = total;
+    for (int round = 0; todo; round++) {
+        RSN_CUDA(cudaMemsetAsync(cnt.p, 0, 4, s));
+        if (round == 0)
+            RSN_LAUNCH(k_resolve4, (unsigned)div_up(todo, kResolveChunk), 256, 0, s, b.sb, b.dist, todo,
+                       wl[0].as<uint32_t>(), cnt.as<uint32_t>());
+        else
+            RSN_LAUNCH(k_resolve, (unsigned)div_up(todo, 256), 256, 0, s, b.sb, b.dist, todo,
+                       wl[(round + 1) & 1].as<uint32_t>(), wl[round & 1].as<uint32_t>(), cnt.as<uint32_t>());
+        RSN_CUDA(cudaMemcpyAsync(c.h_scalars, cnt.p, 4, cudaMemcpyDeviceToHost, s));
+        RSN_CUDA(cudaStreamSynchronize(s));
+        todo = (size_t)(uint32_t)c.h_scalars[0];
+    }
+    RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(DecFile), cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    // ---- phase C: un-escape the files whose literals hold 5C / FF
+    bool any_unesc = false;
+    for (size_t f = 0; f < G; f++) {
+        if (h[f].n && (h[f].flags & ERR_BAD_REF)) {  // a pointer before the start of the output (lzss.go:349)
+            out.rc[f] = RSN_ERR_BAD_REFERENCE;
+            h[f].n = 0;
+        }
+        h[f].unesc = (h[f].n && (h[f].flags & FLAG_NEEDS_UNESCAPE)) ? 1u : 0u;
+        h[f].un_n = h[f].sbn;
+        any_unesc |= h[f].unesc != 0;
+    }
+    DevBuf out2;
+    if (any_unesc) {
+        const size_t ut = div_up(sb_cap, kTile);
+        b.uc_stride = ut + 1;
+        DevBuf agg, ustate, uoff;
+        RSN_TRY(agg.alloc(G * b.uc_stride * sizeof(UnescAgg), s));
+        RSN_TRY(ustate.alloc(G * b.uc_stride, s));
+        RSN_TRY(uoff.alloc(G * b.uc_stride * 8, s));
+        RSN_TRY(out2.alloc_out(total + 256, s));
+        b.agg = agg.as<UnescAgg>();
+        b.ustate = ustate.as<uint8_t>();
+        b.uoff = uoff.as<uint64_t>();
+        b.out2 = out2.as<uint8_t>();
+        RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(DecFile), cudaMemcpyHostToDevice, s));
+        const dim3 ugrid((unsigned)ut, g);
+        RSN_LAUNCH(kb_unesc_reduce, ugrid, kTileThreads, 0, s, b);
+        RSN_LAUNCH(kb_unesc_spine, g, 1024, 0, s, b);
+        RSN_LAUNCH(kb_unesc_apply, ugrid, kTileThreads, 0, s, b);
+        RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(DecFile), cudaMemcpyDeviceToHost, s));
+        RSN_CUDA(cudaStreamSynchronize(s));
+    }
+    for (size_t f = 0; f < G; f++) {
+        if (out.rc[f] != RSN_OK) continue;
+        out.ptr[f] = (h[f].unesc ? out2.as<uint8_t>() : sb.as<uint8_t>()) + h[f].gbase;
+        out.n[f] = h[f].unesc ? h[f].un_n : h[f].sbn;
+    }
+    out.owned.push_back(sb.release());
+    if (out2.p) out.owned.push_back(out2.release());
+    return RSN_OK;
 }
 
 }  // namespace rsn
