@@ -306,7 +306,7 @@ int stage_per_file(Algo a, bool compress, const BatchIO &in, const uint8_t *cons
 
 int stage_batched(Algo a, bool compress, const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s) {
     if (a == ALGO_LZSS) return compress ? lzss_compress_batch(in, out, 4096, s) : lzss_decompress_batch(in, out, s);
-    (void)h_in;
+    if (a == ALGO_HUFFMAN) return compress ? huff_compress_batch(in, out, s) : huff_decompress_batch(in, h_in, out, s);
     return RSN_ERR_UNSUPPORTED;
 }
 

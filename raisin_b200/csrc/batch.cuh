@@ -6,6 +6,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace rsn {
@@ -37,6 +39,10 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s);
 // h_in[f]: host copy of file f's stream (the header is parsed on the host)
 int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s);
 
+// fn(i) for i in [0, count) on up to `threads` host threads (tree building, header parsing)
+template <class F>
+void parallel_for(size_t count, int threads, F fn);
+
 #ifdef __CUDACC__
 // Exclusive scan of `count` u64 values by one CTA; every thread gets the total.  sm: 33 u64.
 __device__ __forceinline__ uint64_t cta_scan_u64(const uint64_t *__restrict__ in, uint64_t *__restrict__ out,
@@ -53,5 +59,26 @@ __device__ __forceinline__ uint64_t cta_scan_u64(const uint64_t *__restrict__ in
     return carry;
 }
 #endif
+
+template <class F>
+void parallel_for(size_t count, int threads, F fn) {
+    if (threads > (int)count) threads = (int)count;
+    if (threads <= 1) {
+        for (size_t i = 0; i < count; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    auto body = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= count) break;
+            fn(i);
+        }
+    };
+    for (int t = 1; t < threads; t++) pool.emplace_back(body);
+    body();
+    for (auto &th : pool) th.join();
+}
 
 }  // namespace rsn

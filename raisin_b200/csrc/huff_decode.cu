@@ -6,11 +6,13 @@
 // Subsequence 0 starts at bit 0, which is exact, so the fixed point is the sequential decode
 // of findCodes (huffman.go:131-153): walk from the root, left on 0 / right on 1, emit at a
 // leaf, restart at the root while bits remain, fail if the bits end inside a code.
+#include "batch.cuh"
 #include "common.cuh"
 #include "huff.cuh"
 #include "huff_host.h"
 #include "utf8.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -366,6 +368,264 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
     (void)c;
     *d_out = (uint8_t *)out.release();
     *out_n = (size_t)total;
+    return RSN_OK;
+}
+
+// ============================================================================= batches of small files
+//
+// Headers are parsed and trees built on the host for every file of the group (in parallel), the
+// tables of all files go up in one copy, and each decode kernel runs once over the group
+// (blockIdx.y = file).  The self-synchronisation loop iterates until no file changes.
+
+struct HdecFile {
+    DecParams p;
+    uint64_t sub_base;   // first subsequence of the file in the group's start/end/cnt arrays
+    uint64_t subs;
+    uint64_t out_base;   // offset of the file's bytes in the group's result buffer
+    uint64_t total;      // decoded bytes
+    uint32_t err, pad;
+};
+
+__global__ void kb_hdec_init(const HdecFile *__restrict__ files, uint64_t *__restrict__ start,
+                             uint64_t *__restrict__ end, uint64_t *__restrict__ cnt) {
+    const HdecFile &f = files[blockIdx.y];
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= f.subs) return;
+    const uint64_t s0 = (uint64_t)t * kSubBits;
+    const uint64_t limit = min((uint64_t)(t + 1) * kSubBits, f.p.max);
+    uint64_t bytes;
+    bool trunc;
+    const uint64_t e = decode_span<false>(f.p, s0, limit, bytes, trunc, nullptr);
+    start[f.sub_base + t] = s0;
+    end[f.sub_base + t] = e;
+    cnt[f.sub_base + t] = bytes;
+}
+
+__global__ void kb_hdec_sync(const HdecFile *__restrict__ files, uint64_t *__restrict__ start,
+                             const uint64_t *__restrict__ end_prev, uint64_t *__restrict__ end_next,
+                             uint64_t *__restrict__ cnt, uint32_t *__restrict__ changed) {
+    const HdecFile &f = files[blockIdx.y];
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= f.subs) return;
+    const size_t g = f.sub_base + t;
+    if (t == 0) {
+        end_next[g] = end_prev[g];
+        return;
+    }
+    const uint64_t s1 = end_prev[g - 1];
+    if (s1 == start[g]) {
+        end_next[g] = end_prev[g];
+        return;
+    }
+    const uint64_t limit = min((uint64_t)(t + 1) * kSubBits, f.p.max);
+    uint64_t bytes = 0;
+    bool trunc;
+    uint64_t e = s1;
+    if (s1 < limit) e = decode_span<false>(f.p, s1, limit, bytes, trunc, nullptr);
+    start[g] = s1;
+    end_next[g] = e;
+    cnt[g] = bytes;
+    *changed = 1;
+}
+
+__global__ void __launch_bounds__(256) kb_hdec_finish(HdecFile *__restrict__ files, const uint64_t *__restrict__ cnt,
+                                                      uint64_t *__restrict__ off) {
+    __shared__ uint64_t sm[33];
+    HdecFile &f = files[blockIdx.x];
+    const uint64_t total = cta_scan_u64(cnt + f.sub_base, off + f.sub_base, (size_t)f.subs, sm);
+    if (threadIdx.x == 0) f.total = total;
+}
+
+__global__ void kb_hdec_write(HdecFile *__restrict__ files, const uint64_t *__restrict__ start,
+                              const uint64_t *__restrict__ off, uint8_t *__restrict__ out) {
+    HdecFile &f = files[blockIdx.y];
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= f.subs) return;
+    const uint64_t limit = min((uint64_t)(t + 1) * kSubBits, f.p.max);
+    const uint64_t s0 = start[f.sub_base + t];
+    if (s0 >= limit) return;
+    uint64_t bytes;
+    bool trunc;
+    decode_span<true>(f.p, s0, limit, bytes, trunc, out + f.out_base + off[f.sub_base + t]);
+    if (trunc) f.err = 1;  // data[i] with i == len(data) (huffman.go:145)
+}
+
+namespace {
+struct HdecHost {           // what the host learns about one file before any kernel runs
+    int rc = RSN_OK;
+    bool per_file = false;  // leave it to huff_decompress_dev (single-leaf trees)
+    size_t pay_off = 0;
+    uint64_t diff = 0, max = 0;
+    HuffTree tree;
+    std::vector<uint32_t> lut;
+};
+
+void hdec_host_plan(const uint8_t *h, size_t n, HdecHost &pl) {
+    ptrdiff_t sp = -1;
+    for (size_t i = 0; i + 1 < n; i++)
+        if (h[i] == 0x5C && h[i + 1] == 0x0A) {  // strings.SplitN(..., 2), huffman.go:261
+            sp = (ptrdiff_t)i;
+            break;
+        }
+    if (sp < 0) {
+        pl.rc = RSN_ERR_NO_SEPARATOR;
+        return;
+    }
+    std::vector<HuffLeaf> leaves;
+    if (!huff_parse_header(h, (size_t)sp, leaves) || leaves.empty()) {
+        pl.rc = RSN_ERR_BAD_HEADER;
+        return;
+    }
+    huff_build_tree(leaves, pl.tree);
+    pl.pay_off = (size_t)sp + 2;
+    const size_t pn = n - pl.pay_off;
+    pl.diff = pn ? h[pl.pay_off] : 0;
+    const uint64_t nbits = pn ? (uint64_t)(pn - 1) * 8 : 0;
+    if (pl.diff > nbits) {
+        pl.rc = RSN_ERR_TRUNCATED;
+        return;
+    }
+    pl.max = nbits - pl.diff;
+    const HuffTree &tree = pl.tree;
+    if (tree.nodes[tree.root].left < 0) {
+        pl.per_file = true;
+        return;
+    }
+    if (pl.max == 0) {
+        pl.rc = RSN_ERR_TRUNCATED;
+        return;
+    }
+    pl.lut.resize((size_t)1 << kLutBits);
+    for (uint32_t idx = 0; idx < pl.lut.size(); idx++) {
+        int32_t node = tree.root;
+        uint32_t len = 0;
+        while (tree.nodes[node].left >= 0 && len < (uint32_t)kLutBits) {
+            const uint32_t bit = (idx >> (kLutBits - 1 - len)) & 1u;
+            node = bit ? tree.nodes[node].right : tree.nodes[node].left;
+            len++;
+        }
+        if (tree.nodes[node].left < 0)
+            pl.lut[idx] = (1u << 31) | (len << 21) | ((uint32_t)tree.nodes[node].right & 0x1FFFFFu);
+        else pl.lut[idx] = (uint32_t)node;
+    }
+}
+}  // namespace
+
+int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s) {
+    const size_t G = in.size();
+    out.resize(G);
+    out.rc = in.rc;
+    if (G == 0) return RSN_OK;
+    if (!h_in) return RSN_ERR_UNSUPPORTED;  // headers are parsed from the host copy of the streams
+    ArenaScope scope(s);
+    std::vector<HdecHost> plan(G);
+    parallel_for(G, 8, [&](size_t f) {
+        if (in.rc[f] != RSN_OK) {
+            plan[f].rc = in.rc[f];
+            return;
+        }
+        hdec_host_plan(h_in[f], (size_t)in.n[f], plan[f]);
+    });
+    // tables of all files in one upload: [nodes | lut] per file
+    std::vector<HdecFile> h(G);
+    std::vector<uint8_t> tab;
+    std::vector<size_t> tab_off(G, 0);
+    size_t subs_total = 0, subs_cap = 1;
+    for (size_t f = 0; f < G; f++) {
+        h[f] = HdecFile{};
+        out.rc[f] = plan[f].rc;
+        if (plan[f].rc != RSN_OK || plan[f].per_file) continue;
+        tab_off[f] = tab.size();
+        const size_t nb = plan[f].tree.nodes.size() * sizeof(HuffNode);
+        const size_t lb = plan[f].lut.size() * 4;
+        tab.resize(tab.size() + ((nb + lb + 255) & ~(size_t)255));
+        memcpy(tab.data() + tab_off[f], plan[f].tree.nodes.data(), nb);
+        memcpy(tab.data() + tab_off[f] + nb, plan[f].lut.data(), lb);
+        h[f].subs = div_up(plan[f].max, kSubBits);
+        h[f].sub_base = subs_total;
+        subs_total += h[f].subs;
+        subs_cap = std::max<size_t>(subs_cap, h[f].subs);
+    }
+    DevBuf dtab, files, start, endA, endB, cnt, off, flag;
+    RSN_TRY(dtab.alloc(tab.size() + 256, s));
+    RSN_TRY(files.alloc(G * sizeof(HdecFile), s));
+    RSN_TRY(start.alloc(subs_total * 8 + 8, s));
+    RSN_TRY(endA.alloc(subs_total * 8 + 8, s));
+    RSN_TRY(endB.alloc(subs_total * 8 + 8, s));
+    RSN_TRY(cnt.alloc(subs_total * 8 + 8, s));
+    RSN_TRY(off.alloc(subs_total * 8 + 8, s));
+    RSN_TRY(flag.alloc(16, s));
+    for (size_t f = 0; f < G; f++) {
+        if (!h[f].subs) continue;
+        DecParams &p = h[f].p;
+        const size_t pn = (size_t)in.n[f] - plan[f].pay_off;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(in.ptr[f] + plan[f].pay_off + 1);
+        p.words = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        p.bit0 = (uint64_t)(addr & 3) * 8 + plan[f].diff;
+        p.nwords = ((addr & 3) + (pn - 1) + 3) / 4;
+        p.max = plan[f].max;
+        const size_t nb = plan[f].tree.nodes.size() * sizeof(HuffNode);
+        p.nodes = reinterpret_cast<const HuffNode *>(dtab.as<uint8_t>() + tab_off[f]);
+        p.lut = reinterpret_cast<const uint32_t *>(dtab.as<uint8_t>() + tab_off[f] + nb);
+        p.root = plan[f].tree.root;
+    }
+    if (!tab.empty()) RSN_CUDA(cudaMemcpyAsync(dtab.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, s));
+    RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HdecFile), cudaMemcpyHostToDevice, s));
+    const dim3 grid((unsigned)div_up(subs_cap, 128), (unsigned)G);
+    Ctx &c = ctx();
+    if (subs_total) {
+        RSN_LAUNCH(kb_hdec_init, grid, 128, 0, s, files.as<HdecFile>(), start.as<uint64_t>(), endA.as<uint64_t>(),
+                   cnt.as<uint64_t>());
+        uint64_t *e_prev = endA.as<uint64_t>(), *e_next = endB.as<uint64_t>();
+        for (size_t iter = 0; iter <= subs_cap; iter++) {
+            RSN_CUDA(cudaMemsetAsync(flag.p, 0, 8, s));
+            RSN_LAUNCH(kb_hdec_sync, grid, 128, 0, s, files.as<HdecFile>(), start.as<uint64_t>(), e_prev, e_next,
+                       cnt.as<uint64_t>(), flag.as<uint32_t>());
+            uint64_t changed = 0;
+            RSN_TRY(read_u64(flag.as<uint64_t>(), &changed, s));
+            std::swap(e_prev, e_next);
+            if (!(uint32_t)changed) break;
+        }
+        RSN_LAUNCH(kb_hdec_finish, (unsigned)G, 256, 0, s, files.as<HdecFile>(), cnt.as<uint64_t>(), off.as<uint64_t>());
+    }
+    RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HdecFile), cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    size_t total = 0;
+    for (size_t f = 0; f < G; f++) {
+        h[f].out_base = total;
+        total += (h[f].total + 16 + 255) & ~(uint64_t)255;
+    }
+    DevBuf res;
+    RSN_TRY(res.alloc_out(total + 256, s));
+    if (subs_total) {
+        RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HdecFile), cudaMemcpyHostToDevice, s));
+        RSN_LAUNCH(kb_hdec_write, grid, 128, 0, s, files.as<HdecFile>(), start.as<uint64_t>(), off.as<uint64_t>(),
+                   res.as<uint8_t>());
+        RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HdecFile), cudaMemcpyDeviceToHost, s));
+    }
+    RSN_CUDA(cudaStreamSynchronize(s));
+    for (size_t f = 0; f < G; f++) {
+        if (out.rc[f] != RSN_OK || plan[f].per_file) continue;
+        if (h[f].err) {
+            out.rc[f] = RSN_ERR_TRUNCATED;
+            continue;
+        }
+        out.ptr[f] = res.as<uint8_t>() + h[f].out_base;
+        out.n[f] = h[f].total;
+    }
+    out.owned.push_back(res.release());
+    // the few files the kernels do not take (single-leaf trees) go through the per-file call
+    for (size_t f = 0; f < G; f++) {
+        if (out.rc[f] != RSN_OK || !plan[f].per_file) continue;
+        uint8_t *r = nullptr;
+        size_t rn = 0;
+        out.rc[f] = huff_decompress_dev(in.ptr[f], (size_t)in.n[f], h_in[f], 0, &r, &rn, s);
+        if (out.rc[f] != RSN_OK) continue;
+        out.ptr[f] = r;
+        out.n[f] = rn;
+        out.owned.push_back(r);
+    }
+    (void)c;
     return RSN_OK;
 }
 

@@ -4,12 +4,14 @@
 //   host   tree + codes + header        (buildTree 58-103, printCodes 110-127, header 312-318)
 //   K10    code-length scan + bit pack  (encode 229-256, AsByteSlice 174-191: MSB-first,
 //                                        pad zero bits in FRONT of the first payload byte)
+#include "batch.cuh"
 #include "common.cuh"
 #include "huff.cuh"
 #include "huff_host.h"
 #include "utf8.cuh"
 
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 namespace rsn {
@@ -127,6 +129,27 @@ struct CodeEntry {
     uint64_t code;
 };
 
+// Codes of runes >= 256: a dense table over the rune space (single stream), or a small
+// open-addressing table per file (batches; every rune looked up is present).
+struct DenseBig {
+    const uint64_t *code;
+    const uint8_t *len;
+    __device__ __forceinline__ uint32_t len_of(int32_t r) const { return __ldg(len + r); }
+    __device__ __forceinline__ uint64_t code_of(int32_t r) const { return __ldg(code + r); }
+};
+__host__ __device__ __forceinline__ uint32_t big_hash(uint32_t rune) { return (rune * 2654435761u) >> 12; }
+struct HashBig {
+    const CodeEntry *tab;
+    uint32_t mask;
+    __device__ __forceinline__ const CodeEntry &find(int32_t r) const {
+        uint32_t h = big_hash((uint32_t)r) & mask;
+        while (tab[h].rune != (uint32_t)r) h = (h + 1) & mask;
+        return tab[h];
+    }
+    __device__ __forceinline__ uint32_t len_of(int32_t r) const { return find(r).len; }
+    __device__ __forceinline__ uint64_t code_of(int32_t r) const { return find(r).code; }
+};
+
 __global__ void k_code_scatter(const CodeEntry *__restrict__ list, size_t k, uint64_t *__restrict__ code,
                                uint8_t *__restrict__ len) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,9 +159,10 @@ __global__ void k_code_scatter(const CodeEntry *__restrict__ list, size_t k, uin
 }
 
 // per-tile total code bits
-__global__ void __launch_bounds__(kTileThreads) k_enc_count(const uint8_t *__restrict__ in, size_t n,
-                                                            const uint8_t *__restrict__ len_tab,
-                                                            uint64_t *__restrict__ tile_bits) {
+template <class Big>
+__device__ __forceinline__ void enc_count_body(const uint8_t *__restrict__ in, size_t n,
+                                               const uint8_t *__restrict__ len_tab, const Big big,
+                                               uint64_t *__restrict__ tile_bits) {
     __shared__ uint8_t slen[kSmallBins];
     __shared__ uint32_t sm[33];
     for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x) slen[i] = len_tab[i];
@@ -151,11 +175,17 @@ __global__ void __launch_bounds__(kTileThreads) k_enc_count(const uint8_t *__res
         const uint32_t startmask = classify16(in, base, n, valid, runes);
 #pragma unroll
         for (int k = 0; k < 16; k++)
-            if (startmask & (1u << k)) bits += runes[k] < kSmallBins ? slen[runes[k]] : __ldg(len_tab + runes[k]);
+            if (startmask & (1u << k)) bits += runes[k] < kSmallBins ? slen[runes[k]] : big.len_of(runes[k]);
     }
     uint32_t total;
     block_exclusive_sum<uint32_t>(bits, sm, total);
     if (threadIdx.x == 0) tile_bits[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kTileThreads) k_enc_count(const uint8_t *__restrict__ in, size_t n,
+                                                            const uint8_t *__restrict__ len_tab,
+                                                            const uint64_t *__restrict__ code_tab,
+                                                            uint64_t *__restrict__ tile_bits) {
+    enc_count_body(in, n, len_tab, DenseBig{code_tab, len_tab}, tile_bits);
 }
 
 // MSB-first bit writer over a zero-initialised, 4-byte aligned output: partially covered words
@@ -200,12 +230,12 @@ struct BitWriter {
 
 // PACKED: every code is at most 24 bits long; runes < 256 then come from a shared table of
 // (len << 24 | code) words and the bits of a thread are assembled in one 64-bit register.
-template <bool PACKED>
-__global__ void __launch_bounds__(kTileThreads) k_enc_write(const uint8_t *__restrict__ in, size_t n,
-                                                            const uint64_t *__restrict__ code_tab,
-                                                            const uint8_t *__restrict__ len_tab,
-                                                            const uint64_t *__restrict__ tile_bitoff,
-                                                            uint64_t bit_base, uint32_t *__restrict__ out) {
+template <bool PACKED, class Big>
+__device__ __forceinline__ void enc_write_body(const uint8_t *__restrict__ in, size_t n,
+                                               const uint64_t *__restrict__ code_tab,
+                                               const uint8_t *__restrict__ len_tab, const Big big,
+                                               const uint64_t *__restrict__ tile_bitoff, uint64_t bit_base,
+                                               uint32_t *__restrict__ out) {
     __shared__ uint8_t slen[PACKED ? 1 : kSmallBins];
     __shared__ uint64_t scode[PACKED ? 1 : kSmallBins];
     __shared__ uint32_t spack[PACKED ? kSmallBins : 1];
@@ -231,10 +261,10 @@ __global__ void __launch_bounds__(kTileThreads) k_enc_write(const uint8_t *__res
             if (startmask & (1u << k)) {
                 const int32_t r = runes[k];
                 if (PACKED) {
-                    ent[k] = r < kSmallBins ? spack[r] : (((uint32_t)__ldg(len_tab + r) << 24) | (uint32_t)__ldg(code_tab + r));
+                    ent[k] = r < kSmallBins ? spack[r] : ((big.len_of(r) << 24) | (uint32_t)big.code_of(r));
                     bits += ent[k] >> 24;
                 } else {
-                    bits += r < kSmallBins ? slen[r] : __ldg(len_tab + r);
+                    bits += r < kSmallBins ? slen[r] : big.len_of(r);
                 }
             }
         }
@@ -277,10 +307,18 @@ __global__ void __launch_bounds__(kTileThreads) k_enc_write(const uint8_t *__res
         if (startmask & (1u << k)) {
             const int32_t r = runes[k];
             if (r < kSmallBins) bw.put(scode[r], slen[r]);
-            else bw.put(__ldg(code_tab + r), __ldg(len_tab + r));
+            else bw.put(big.code_of(r), big.len_of(r));
         }
     }
     bw.finish();
+}
+template <bool PACKED>
+__global__ void __launch_bounds__(kTileThreads) k_enc_write(const uint8_t *__restrict__ in, size_t n,
+                                                            const uint64_t *__restrict__ code_tab,
+                                                            const uint8_t *__restrict__ len_tab,
+                                                            const uint64_t *__restrict__ tile_bitoff,
+                                                            uint64_t bit_base, uint32_t *__restrict__ out) {
+    enc_write_body<PACKED>(in, n, code_tab, len_tab, DenseBig{code_tab, len_tab}, tile_bitoff, bit_base, out);
 }
 
 // ============================================================================= host orchestration
@@ -356,7 +394,8 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
         DevBuf tb, tbo;
         RSN_TRY(tb.alloc(tiles * 8, s));
         RSN_TRY(tbo.alloc((tiles + 1) * 8, s));
-        RSN_LAUNCH(k_enc_count, (unsigned)tiles, kTileThreads, 0, s, d_in, n, len_tab.as<uint8_t>(), tb.as<uint64_t>());
+        RSN_LAUNCH(k_enc_count, (unsigned)tiles, kTileThreads, 0, s, d_in, n, len_tab.as<uint8_t>(),
+                   code_tab.as<uint64_t>(), tb.as<uint64_t>());
         RSN_TRY(spine_scan_u64(tb.as<uint64_t>(), tbo.as<uint64_t>(), tbo.as<uint64_t>() + tiles, tiles, s));
         if (maxlen <= 24)
             RSN_LAUNCH(k_enc_write<true>, (unsigned)tiles, kTileThreads, 0, s, d_in, n, code_tab.as<uint64_t>(),
@@ -371,6 +410,303 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     (void)c;
     *d_out = (uint8_t *)out.release();
     *out_n = total;
+    return RSN_OK;
+}
+
+// ============================================================================= batches of small files
+//
+// One launch per kernel for a group of files (batch.cuh).  A dense table over the rune space per
+// file would cost far more than the file itself, so: runes below 256 are counted in 256 bins per
+// file, U+FFFD in a counter, and the remaining runes (multi-byte UTF-8 in binary-looking data) are
+// appended to a per-file list that the host sorts and counts.  Trees, codes and headers are built on
+// the host for every file (in parallel), the code tables of all files go up in one copy, codes of
+// runes >= 256 in a small hash table per file.
+
+constexpr int kHistTilesPerCta = 8;
+constexpr int kHistStride = 260;  // 256 bins, [256] = U+FFFD
+
+struct HencFile {
+    const uint8_t *in;
+    uint64_t n;
+    uint32_t big_n;       // runes appended to the file's list (phase 1)
+    uint32_t packed;      // every code is at most 24 bits long
+    const uint64_t *scode;  // codes / lengths of runes < 256
+    const uint8_t *slen;
+    const CodeEntry *btab;  // hash table of the other runes
+    uint32_t bmask, pad;
+    uint32_t *out_words;  // 4-byte aligned start of the file's output
+    uint64_t bit_base;    // first code bit: 8 * (header + 5C 0A + pad byte) + pad
+    const uint8_t *prefix;
+    uint64_t prefix_n;
+};
+
+struct HencBatch {
+    HencFile *files;
+    uint32_t *hist;        // [G][kHistStride]
+    uint32_t *big;         // [G][big_stride]
+    size_t big_stride;
+    uint64_t *tile_bits, *tile_off;  // [G][tc_stride]
+    size_t tc_stride;
+};
+
+__global__ void __launch_bounds__(kTileThreads) kb_rune_hist(HencBatch b) {
+    __shared__ uint32_t bins[kHistCopies][kSmallBins];
+    __shared__ uint32_t fffd_sm;
+    HencFile &f = b.files[blockIdx.y];
+    const size_t n = (size_t)f.n;
+    const size_t tile0 = (size_t)blockIdx.x * kHistTilesPerCta;
+    if (tile0 * kTile >= n) return;
+    for (int i = threadIdx.x; i < kHistCopies * kSmallBins; i += blockDim.x) (&bins[0][0])[i] = 0;
+    if (threadIdx.x == 0) fffd_sm = 0;
+    __syncthreads();
+    uint32_t *mybins = bins[threadIdx.x & (kHistCopies - 1)];
+    uint32_t *biglist = b.big + (size_t)blockIdx.y * b.big_stride;
+    uint32_t fffd = 0;
+    for (int q = 0; q < kHistTilesPerCta; q++) {
+        const size_t base = (tile0 + q) * kTile + (size_t)threadIdx.x * kItems;
+        if (base >= n) break;
+        const int valid = (int)min((size_t)16, n - base);
+        int32_t runes[16];
+        const uint32_t startmask = classify16(f.in, base, n, valid, runes);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (startmask & (1u << k)) {
+                const int32_t r = runes[k];
+                if (r < kSmallBins) atomicAdd(&mybins[r], 1u);
+                else if (r == 0xFFFD) fffd++;
+                else biglist[atomicAdd(&f.big_n, 1u)] = (uint32_t)r;
+            }
+        }
+    }
+    for (int d = 16; d; d >>= 1) fffd += __shfl_down_sync(0xffffffffu, fffd, d);
+    if (lane_id() == 0 && fffd) atomicAdd(&fffd_sm, fffd);
+    __syncthreads();
+    uint32_t *hist = b.hist + (size_t)blockIdx.y * kHistStride;
+    for (int i = threadIdx.x; i < kSmallBins; i += blockDim.x) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int c = 0; c < kHistCopies; c++) v += bins[c][i];
+        if (v) atomicAdd(&hist[i], v);
+    }
+    if (threadIdx.x == 0 && fffd_sm) atomicAdd(&hist[256], fffd_sm);
+}
+
+__global__ void __launch_bounds__(256) kb_enc_prefix(HencBatch b) {
+    const HencFile &f = b.files[blockIdx.x];
+    uint8_t *dst = reinterpret_cast<uint8_t *>(f.out_words);
+    for (uint64_t i = threadIdx.x; i < f.prefix_n; i += blockDim.x) dst[i] = f.prefix[i];
+}
+
+__global__ void __launch_bounds__(kTileThreads) kb_enc_count(HencBatch b) {
+    const HencFile &f = b.files[blockIdx.y];
+    if ((size_t)blockIdx.x * kTile >= f.n) return;
+    enc_count_body(f.in, (size_t)f.n, f.slen, HashBig{f.btab, f.bmask}, b.tile_bits + (size_t)blockIdx.y * b.tc_stride);
+}
+
+__global__ void __launch_bounds__(256) kb_enc_finish(HencBatch b) {
+    __shared__ uint64_t sm[33];
+    const HencFile &f = b.files[blockIdx.x];
+    const size_t o = (size_t)blockIdx.x * b.tc_stride;
+    cta_scan_u64(b.tile_bits + o, b.tile_off + o, div_up_dev((size_t)f.n, (size_t)kTile), sm);
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(kTileThreads) kb_enc_write(HencBatch b) {
+    const HencFile &f = b.files[blockIdx.y];
+    if ((f.packed != 0) != PACKED || (size_t)blockIdx.x * kTile >= f.n) return;
+    enc_write_body<PACKED>(f.in, (size_t)f.n, f.scode, f.slen, HashBig{f.btab, f.bmask},
+                           b.tile_off + (size_t)blockIdx.y * b.tc_stride, f.bit_base, f.out_words);
+}
+
+namespace {
+struct HencHost {
+    int rc = RSN_OK;
+    std::vector<uint8_t> prefix;      // header | 5C 0A | pad byte
+    std::vector<uint64_t> scode;      // 256
+    std::vector<uint8_t> slen;        // 256
+    std::vector<CodeEntry> btab;      // power-of-two hash table (rune 0xFFFFFFFF = empty)
+    uint64_t total_bits = 0, total = 0;
+    uint32_t pad = 0, maxlen = 0;
+};
+
+void henc_host_plan(const uint32_t *hist, std::vector<uint32_t> &big, HencHost &pl) {
+    std::vector<HuffLeaf> leaves;
+    for (int r = 0; r < kSmallBins; r++)
+        if (hist[r]) leaves.push_back(HuffLeaf{(int64_t)hist[r], r});
+    std::sort(big.begin(), big.end());
+    bool fffd_done = hist[256] == 0;
+    for (size_t i = 0; i < big.size();) {
+        size_t j = i;
+        while (j < big.size() && big[j] == big[i]) j++;
+        if (!fffd_done && big[i] > 0xFFFDu) {
+            leaves.push_back(HuffLeaf{(int64_t)hist[256], 0xFFFD});
+            fffd_done = true;
+        }
+        leaves.push_back(HuffLeaf{(int64_t)(j - i), (int32_t)big[i]});
+        i = j;
+    }
+    if (!fffd_done) leaves.push_back(HuffLeaf{(int64_t)hist[256], 0xFFFD});
+    if (leaves.empty()) {
+        pl.rc = RSN_ERR_EMPTY_INPUT;
+        return;
+    }
+    HuffTree tree;
+    huff_build_tree(leaves, tree);
+    std::vector<HuffCode> codes;
+    if (!huff_codes(tree, codes)) {
+        pl.rc = RSN_ERR_UNSUPPORTED;  // a code longer than 64 bits
+        return;
+    }
+    huff_header(leaves, pl.prefix);
+    pl.scode.assign(kSmallBins, 0);
+    pl.slen.assign(kSmallBins, 0);
+    size_t nbig = 0;
+    for (const HuffCode &cd : codes) {
+        pl.total_bits += (uint64_t)cd.len * (uint64_t)cd.freq;
+        pl.maxlen = std::max<uint32_t>(pl.maxlen, cd.len);
+        if (cd.rune < kSmallBins) {
+            pl.scode[cd.rune] = cd.code;
+            pl.slen[cd.rune] = cd.len;
+        } else {
+            nbig++;
+        }
+    }
+    size_t cap = 2;
+    while (cap < 2 * nbig) cap <<= 1;
+    pl.btab.assign(cap, CodeEntry{0xFFFFFFFFu, 0, 0});
+    for (const HuffCode &cd : codes) {
+        if (cd.rune < kSmallBins) continue;
+        uint32_t h = big_hash((uint32_t)cd.rune) & (uint32_t)(cap - 1);
+        while (pl.btab[h].rune != 0xFFFFFFFFu) h = (h + 1) & (uint32_t)(cap - 1);
+        pl.btab[h] = CodeEntry{(uint32_t)cd.rune, cd.len, cd.code};
+    }
+    pl.pad = (uint32_t)((8 - pl.total_bits % 8) % 8);  // huffman.go:245-249
+    pl.prefix.push_back(0x5C);
+    pl.prefix.push_back(0x0A);
+    pl.prefix.push_back((uint8_t)pl.pad);
+    pl.total = pl.prefix.size() + (pl.total_bits + pl.pad) / 8;
+}
+}  // namespace
+
+int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
+    const size_t G = in.size();
+    out.resize(G);
+    out.rc = in.rc;
+    if (G == 0) return RSN_OK;
+    ArenaScope scope(s);
+    size_t cap = 1;
+    for (size_t f = 0; f < G; f++) {
+        if (in.rc[f] != RSN_OK) continue;
+        if (in.n[f] == 0) out.rc[f] = RSN_ERR_EMPTY_INPUT;  // heap.Pop on an empty heap panics
+        cap = std::max<size_t>(cap, in.n[f]);
+    }
+    if (cap > kBatchMaxFile) return RSN_ERR_UNSUPPORTED;
+    const size_t tiles_cap = div_up(cap, kTile);
+    HencBatch b{};
+    b.big_stride = cap / 2 + 16;
+    b.tc_stride = tiles_cap + 1;
+    std::vector<HencFile> h(G);
+    for (size_t f = 0; f < G; f++) {
+        h[f] = HencFile{};
+        h[f].in = in.ptr[f];
+        h[f].n = out.rc[f] == RSN_OK ? in.n[f] : 0;
+    }
+    DevBuf files, hist, big, tb, tbo;
+    RSN_TRY(files.alloc(G * sizeof(HencFile), s));
+    RSN_TRY(hist.alloc(G * kHistStride * 4, s));
+    RSN_TRY(big.alloc(G * b.big_stride * 4, s));
+    RSN_TRY(tb.alloc(G * b.tc_stride * 8, s));
+    RSN_TRY(tbo.alloc(G * b.tc_stride * 8, s));
+    b.files = files.as<HencFile>();
+    b.hist = hist.as<uint32_t>();
+    b.big = big.as<uint32_t>();
+    b.tile_bits = tb.as<uint64_t>();
+    b.tile_off = tbo.as<uint64_t>();
+    const unsigned g = (unsigned)G;
+    // ---- phase 1: histograms
+    RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HencFile), cudaMemcpyHostToDevice, s));
+    RSN_CUDA(cudaMemsetAsync(hist.p, 0, G * kHistStride * 4, s));
+    RSN_LAUNCH(kb_rune_hist, dim3((unsigned)div_up(tiles_cap, kHistTilesPerCta), g), kTileThreads, 0, s, b);
+    std::vector<uint32_t> h_hist(G * kHistStride);
+    RSN_CUDA(cudaMemcpyAsync(h_hist.data(), hist.p, G * kHistStride * 4, cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HencFile), cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    std::vector<std::vector<uint32_t>> h_big(G);
+    for (size_t f = 0; f < G; f++) {
+        if (!h[f].big_n) continue;
+        h_big[f].resize(h[f].big_n);
+        RSN_CUDA(cudaMemcpyAsync(h_big[f].data(), b.big + f * b.big_stride, (size_t)h[f].big_n * 4,
+                                 cudaMemcpyDeviceToHost, s));
+    }
+    RSN_CUDA(cudaStreamSynchronize(s));
+    // ---- host: tree, codes, header per file (exactly as the reference builds them)
+    std::vector<HencHost> plan(G);
+    parallel_for(G, 8, [&](size_t f) {
+        if (out.rc[f] != RSN_OK) {
+            plan[f].rc = out.rc[f];
+            return;
+        }
+        henc_host_plan(h_hist.data() + f * kHistStride, h_big[f], plan[f]);
+    });
+    // ---- tables and prefixes of all files in one upload; one result buffer
+    std::vector<uint8_t> tab;
+    std::vector<size_t> o_code(G), o_len(G), o_btab(G), o_pre(G);
+    auto put = [&](const void *src, size_t bytes) {
+        const size_t at = (tab.size() + 15) & ~(size_t)15;
+        tab.resize(at + bytes);
+        memcpy(tab.data() + at, src, bytes);
+        return at;
+    };
+    size_t total = 0;
+    std::vector<size_t> out_base(G, 0);
+    bool any_packed = false, any_wide = false;
+    for (size_t f = 0; f < G; f++) {
+        out.rc[f] = plan[f].rc;
+        if (plan[f].rc != RSN_OK) continue;
+        o_code[f] = put(plan[f].scode.data(), kSmallBins * 8);
+        o_len[f] = put(plan[f].slen.data(), kSmallBins);
+        o_btab[f] = put(plan[f].btab.data(), plan[f].btab.size() * sizeof(CodeEntry));
+        o_pre[f] = put(plan[f].prefix.data(), plan[f].prefix.size());
+        out_base[f] = total;
+        total += (plan[f].total + 16 + 255) & ~(size_t)255;
+        (plan[f].maxlen <= 24 ? any_packed : any_wide) = true;
+    }
+    DevBuf dtab, res;
+    RSN_TRY(dtab.alloc(tab.size() + 256, s));
+    RSN_TRY(res.alloc_out(total + 256, s));
+    for (size_t f = 0; f < G; f++) {
+        HencFile &r = h[f];
+        if (plan[f].rc != RSN_OK) {
+            r.n = 0;
+            continue;
+        }
+        r.packed = plan[f].maxlen <= 24;
+        r.scode = reinterpret_cast<const uint64_t *>(dtab.as<uint8_t>() + o_code[f]);
+        r.slen = dtab.as<uint8_t>() + o_len[f];
+        r.btab = reinterpret_cast<const CodeEntry *>(dtab.as<uint8_t>() + o_btab[f]);
+        r.bmask = (uint32_t)(plan[f].btab.size() - 1);
+        r.out_words = reinterpret_cast<uint32_t *>(res.as<uint8_t>() + out_base[f]);
+        r.bit_base = (uint64_t)plan[f].prefix.size() * 8 + plan[f].pad;
+        r.prefix = dtab.as<uint8_t>() + o_pre[f];
+        r.prefix_n = plan[f].prefix.size();
+    }
+    if (!tab.empty()) RSN_CUDA(cudaMemcpyAsync(dtab.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, s));
+    RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HencFile), cudaMemcpyHostToDevice, s));
+    RSN_CUDA(cudaMemsetAsync(res.p, 0, total + 256, s));
+    // ---- phase 2: code-length scan and bit pack
+    const dim3 tgrid((unsigned)tiles_cap, g);
+    RSN_LAUNCH(kb_enc_prefix, g, 256, 0, s, b);
+    RSN_LAUNCH(kb_enc_count, tgrid, kTileThreads, 0, s, b);
+    RSN_LAUNCH(kb_enc_finish, g, 256, 0, s, b);
+    if (any_packed) RSN_LAUNCH(kb_enc_write<true>, tgrid, kTileThreads, 0, s, b);
+    if (any_wide) RSN_LAUNCH(kb_enc_write<false>, tgrid, kTileThreads, 0, s, b);
+    RSN_CUDA(cudaStreamSynchronize(s));  // tab / h are read by the copies above
+    for (size_t f = 0; f < G; f++) {
+        if (out.rc[f] != RSN_OK) continue;
+        out.ptr[f] = res.as<uint8_t>() + out_base[f];
+        out.n[f] = plan[f].total;
+    }
+    out.owned.push_back(res.release());
     return RSN_OK;
 }
 
