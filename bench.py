@@ -241,7 +241,7 @@ def main():
     ap.add_argument("--workload", default="stream", choices=["stream", "batch"],
                     help="stream: BASELINE configs[1] (default, the headline); batch: configs[3] shape")
     ap.add_argument("--files", type=int, default=512, help="batch workload: files per GPU (256 KiB each)")
-    ap.add_argument("--workers", type=int, default=16)
+    ap.add_argument("--workers", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -5,6 +5,7 @@
 #include "huff.cuh"
 #include "lzss.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -276,6 +277,10 @@ extern "C" {
 }  // extern "C"
 
 namespace rsn {
+static std::atomic<int> g_batch_host_threads{4};
+int batch_host_threads() { return g_batch_host_threads.load(); }
+void set_batch_host_threads(int t) { g_batch_host_threads.store(t < 1 ? 1 : t); }
+
 namespace {
 
 // One stage over a group, file by file (stages without a batched implementation, or groups the
@@ -315,6 +320,7 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
                 const uint8_t *const *in, const size_t *in_n, uint8_t **out, size_t *out_n, int *rcs, cudaStream_t s) {
     const size_t G = idx.size();
     ArenaScope scope(s);
+    Trace tr("batch", s);
     BatchIO cur;
     cur.resize(G);
     size_t total = 0;
@@ -331,6 +337,7 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
         if (in_n[i]) RSN_CUDA(cudaMemcpyAsync(d.as<uint8_t>() + off, in[i], in_n[i], cudaMemcpyHostToDevice, s));
         off += (in_n[i] + 64 + 255) & ~(size_t)255;
     }
+    tr.mark("h2d");
     const size_t k = algos.size();
     for (size_t step = 0; step < k; step++) {
         const Algo a = compress ? algos[step] : algos[k - 1 - step];
@@ -347,6 +354,7 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
             return rc;
         }
         cur = std::move(next);
+        tr.mark(a == ALGO_LZSS ? "lzss stage" : "huffman stage");
     }
     // device -> host: all copies queued, one synchronisation
     int rc = RSN_OK;
@@ -372,6 +380,7 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) rc = cuda_fail(e, "batch d2h sync", __FILE__, __LINE__);
     cur.release(s);
+    tr.mark("d2h");
     return rc;
 }
 
@@ -391,14 +400,14 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
     RSN_TRY(parse_layers(algorithms, algos));
     RSN_TRY(ensure_ctx());
     const int dev = ctx().device;
-    if (workers <= 0) workers = 16;
+    if (workers <= 0) workers = 6;
     std::vector<int> rc_local;
     if (!rcs) {
         rc_local.assign(count ? count : 1, RSN_OK);
         rcs = rc_local.data();
     }
     // groups of small files
-    constexpr size_t kGroupBytes = (size_t)64 << 20, kGroupFiles = 1024;
+    constexpr size_t kGroupBytes = (size_t)16 << 20, kGroupFiles = 512;
     std::vector<std::vector<size_t>> groups;
     std::vector<size_t> singles;
     if (!device) {
@@ -420,6 +429,10 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
     }
     const size_t units = groups.size() + singles.size();
     if ((size_t)workers > units) workers = (int)(units ? units : 1);
+    {
+        const int hw = (int)std::thread::hardware_concurrency();
+        set_batch_host_threads(std::max(2, (hw > 0 ? hw : 8) / workers));
+    }
     std::atomic<size_t> next{0};
     std::atomic<int> first_err{RSN_OK};
     auto note = [&](int rc) {

@@ -39,6 +39,11 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s);
 // h_in[f]: host copy of file f's stream (the header is parsed on the host)
 int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s);
 
+// host threads one group may use for its per-file host work (set per batch call from the core count
+// and the number of group workers)
+int batch_host_threads();
+void set_batch_host_threads(int t);
+
 // fn(i) for i in [0, count) on up to `threads` host threads (tree building, header parsing)
 template <class F>
 void parallel_for(size_t count, int threads, F fn);

@@ -457,8 +457,22 @@ struct HdecHost {           // what the host learns about one file before any ke
     size_t pay_off = 0;
     uint64_t diff = 0, max = 0;
     HuffTree tree;
-    std::vector<uint32_t> lut;
 };
+
+// lookup table over the first kLutBits bits of a code, written into the group's staging buffer
+void hdec_fill_lut(const HuffTree &tree, uint32_t *lut) {
+    for (uint32_t idx = 0; idx < (1u << kLutBits); idx++) {
+        int32_t node = tree.root;
+        uint32_t len = 0;
+        while (tree.nodes[node].left >= 0 && len < (uint32_t)kLutBits) {
+            const uint32_t bit = (idx >> (kLutBits - 1 - len)) & 1u;
+            node = bit ? tree.nodes[node].right : tree.nodes[node].left;
+            len++;
+        }
+        if (tree.nodes[node].left < 0) lut[idx] = (1u << 31) | (len << 21) | ((uint32_t)tree.nodes[node].right & 0x1FFFFFu);
+        else lut[idx] = (uint32_t)node;
+    }
+}
 
 void hdec_host_plan(const uint8_t *h, size_t n, HdecHost &pl) {
     ptrdiff_t sp = -1;
@@ -495,19 +509,6 @@ void hdec_host_plan(const uint8_t *h, size_t n, HdecHost &pl) {
         pl.rc = RSN_ERR_TRUNCATED;
         return;
     }
-    pl.lut.resize((size_t)1 << kLutBits);
-    for (uint32_t idx = 0; idx < pl.lut.size(); idx++) {
-        int32_t node = tree.root;
-        uint32_t len = 0;
-        while (tree.nodes[node].left >= 0 && len < (uint32_t)kLutBits) {
-            const uint32_t bit = (idx >> (kLutBits - 1 - len)) & 1u;
-            node = bit ? tree.nodes[node].right : tree.nodes[node].left;
-            len++;
-        }
-        if (tree.nodes[node].left < 0)
-            pl.lut[idx] = (1u << 31) | (len << 21) | ((uint32_t)tree.nodes[node].right & 0x1FFFFFu);
-        else pl.lut[idx] = (uint32_t)node;
-    }
 }
 }  // namespace
 
@@ -518,36 +519,45 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
     if (G == 0) return RSN_OK;
     if (!h_in) return RSN_ERR_UNSUPPORTED;  // headers are parsed from the host copy of the streams
     ArenaScope scope(s);
+    Trace tr("hd batch", s);
     std::vector<HdecHost> plan(G);
-    parallel_for(G, 8, [&](size_t f) {
+    parallel_for(G, batch_host_threads(), [&](size_t f) {
         if (in.rc[f] != RSN_OK) {
             plan[f].rc = in.rc[f];
             return;
         }
         hdec_host_plan(h_in[f], (size_t)in.n[f], plan[f]);
     });
+    tr.mark("host headers+trees");
     // tables of all files in one upload: [nodes | lut] per file
     std::vector<HdecFile> h(G);
-    std::vector<uint8_t> tab;
+    static thread_local std::vector<uint8_t> tab;  // keeps its pages between groups
     std::vector<size_t> tab_off(G, 0);
+    size_t tab_n = 0;
+    const size_t lb = ((size_t)1 << kLutBits) * 4;
     size_t subs_total = 0, subs_cap = 1;
     for (size_t f = 0; f < G; f++) {
         h[f] = HdecFile{};
         out.rc[f] = plan[f].rc;
         if (plan[f].rc != RSN_OK || plan[f].per_file) continue;
-        tab_off[f] = tab.size();
+        tab_off[f] = tab_n;
         const size_t nb = plan[f].tree.nodes.size() * sizeof(HuffNode);
-        const size_t lb = plan[f].lut.size() * 4;
-        tab.resize(tab.size() + ((nb + lb + 255) & ~(size_t)255));
-        memcpy(tab.data() + tab_off[f], plan[f].tree.nodes.data(), nb);
-        memcpy(tab.data() + tab_off[f] + nb, plan[f].lut.data(), lb);
+        tab_n += (nb + lb + 255) & ~(size_t)255;
         h[f].subs = div_up(plan[f].max, kSubBits);
         h[f].sub_base = subs_total;
         subs_total += h[f].subs;
         subs_cap = std::max<size_t>(subs_cap, h[f].subs);
     }
+    if (tab.size() < tab_n) tab.resize(tab_n);
+    uint8_t *const tabp = tab.data();  // (a thread_local name inside the lambda would be the helper thread's own)
+    parallel_for(G, batch_host_threads(), [&, tabp](size_t f) {
+        if (!h[f].subs) return;
+        const size_t nb = plan[f].tree.nodes.size() * sizeof(HuffNode);
+        memcpy(tabp + tab_off[f], plan[f].tree.nodes.data(), nb);
+        hdec_fill_lut(plan[f].tree, reinterpret_cast<uint32_t *>(tabp + tab_off[f] + nb));
+    });
     DevBuf dtab, files, start, endA, endB, cnt, off, flag;
-    RSN_TRY(dtab.alloc(tab.size() + 256, s));
+    RSN_TRY(dtab.alloc(tab_n + 256, s));
     RSN_TRY(files.alloc(G * sizeof(HdecFile), s));
     RSN_TRY(start.alloc(subs_total * 8 + 8, s));
     RSN_TRY(endA.alloc(subs_total * 8 + 8, s));
@@ -569,10 +579,11 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         p.lut = reinterpret_cast<const uint32_t *>(dtab.as<uint8_t>() + tab_off[f] + nb);
         p.root = plan[f].tree.root;
     }
-    if (!tab.empty()) RSN_CUDA(cudaMemcpyAsync(dtab.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, s));
+    if (tab_n) RSN_CUDA(cudaMemcpyAsync(dtab.p, tabp, tab_n, cudaMemcpyHostToDevice, s));
     RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HdecFile), cudaMemcpyHostToDevice, s));
     const dim3 grid((unsigned)div_up(subs_cap, 128), (unsigned)G);
     Ctx &c = ctx();
+    tr.mark("tables");
     if (subs_total) {
         RSN_LAUNCH(kb_hdec_init, grid, 128, 0, s, files.as<HdecFile>(), start.as<uint64_t>(), endA.as<uint64_t>(),
                    cnt.as<uint64_t>());
@@ -590,6 +601,7 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
     }
     RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HdecFile), cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaStreamSynchronize(s));
+    tr.mark("init+sync");
     size_t total = 0;
     for (size_t f = 0; f < G; f++) {
         h[f].out_base = total;
@@ -604,6 +616,7 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HdecFile), cudaMemcpyDeviceToHost, s));
     }
     RSN_CUDA(cudaStreamSynchronize(s));
+    tr.mark("write");
     for (size_t f = 0; f < G; f++) {
         if (out.rc[f] != RSN_OK || plan[f].per_file) continue;
         if (h[f].err) {

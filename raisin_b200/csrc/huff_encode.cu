@@ -522,18 +522,55 @@ namespace {
 struct HencHost {
     int rc = RSN_OK;
     std::vector<uint8_t> prefix;      // header | 5C 0A | pad byte
-    std::vector<uint64_t> scode;      // 256
-    std::vector<uint8_t> slen;        // 256
-    std::vector<CodeEntry> btab;      // power-of-two hash table (rune 0xFFFFFFFF = empty)
+    std::vector<HuffCode> codes;
+    size_t btab_cap = 2;              // power-of-two hash table size for the runes >= 256
     uint64_t total_bits = 0, total = 0;
     uint32_t pad = 0, maxlen = 0;
 };
+
+// the file's device tables, written straight into the group's staging buffer
+void henc_fill_tables(const HencHost &pl, uint64_t *scode, uint8_t *slen, CodeEntry *btab) {
+    for (int i = 0; i < kSmallBins; i++) {
+        scode[i] = 0;
+        slen[i] = 0;
+    }
+    for (size_t i = 0; i < pl.btab_cap; i++) btab[i] = CodeEntry{0xFFFFFFFFu, 0, 0};  // empty
+    const uint32_t mask = (uint32_t)(pl.btab_cap - 1);
+    for (const HuffCode &cd : pl.codes) {
+        if (cd.rune < kSmallBins) {
+            scode[cd.rune] = cd.code;
+            slen[cd.rune] = cd.len;
+            continue;
+        }
+        uint32_t h = big_hash((uint32_t)cd.rune) & mask;
+        while (btab[h].rune != 0xFFFFFFFFu) h = (h + 1) & mask;
+        btab[h] = CodeEntry{(uint32_t)cd.rune, cd.len, cd.code};
+    }
+}
+
+// runes are below 2^21: three byte-wise counting passes
+void sort_runes(std::vector<uint32_t> &v) {
+    if (v.size() < 256) {
+        std::sort(v.begin(), v.end());
+        return;
+    }
+    std::vector<uint32_t> tmp(v.size());
+    uint32_t *src = v.data(), *dst = tmp.data();
+    for (int byte = 0; byte < 3; byte++) {
+        size_t cnt[257] = {0};
+        for (size_t i = 0; i < v.size(); i++) cnt[((src[i] >> (8 * byte)) & 0xFF) + 1]++;
+        for (int d = 0; d < 256; d++) cnt[d + 1] += cnt[d];
+        for (size_t i = 0; i < v.size(); i++) dst[cnt[(src[i] >> (8 * byte)) & 0xFF]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != v.data()) std::copy(src, src + v.size(), v.data());
+}
 
 void henc_host_plan(const uint32_t *hist, std::vector<uint32_t> &big, HencHost &pl) {
     std::vector<HuffLeaf> leaves;
     for (int r = 0; r < kSmallBins; r++)
         if (hist[r]) leaves.push_back(HuffLeaf{(int64_t)hist[r], r});
-    std::sort(big.begin(), big.end());
+    sort_runes(big);
     bool fffd_done = hist[256] == 0;
     for (size_t i = 0; i < big.size();) {
         size_t j = i;
@@ -552,34 +589,18 @@ void henc_host_plan(const uint32_t *hist, std::vector<uint32_t> &big, HencHost &
     }
     HuffTree tree;
     huff_build_tree(leaves, tree);
-    std::vector<HuffCode> codes;
-    if (!huff_codes(tree, codes)) {
+    if (!huff_codes(tree, pl.codes)) {
         pl.rc = RSN_ERR_UNSUPPORTED;  // a code longer than 64 bits
         return;
     }
     huff_header(leaves, pl.prefix);
-    pl.scode.assign(kSmallBins, 0);
-    pl.slen.assign(kSmallBins, 0);
     size_t nbig = 0;
-    for (const HuffCode &cd : codes) {
+    for (const HuffCode &cd : pl.codes) {
         pl.total_bits += (uint64_t)cd.len * (uint64_t)cd.freq;
         pl.maxlen = std::max<uint32_t>(pl.maxlen, cd.len);
-        if (cd.rune < kSmallBins) {
-            pl.scode[cd.rune] = cd.code;
-            pl.slen[cd.rune] = cd.len;
-        } else {
-            nbig++;
-        }
+        if (cd.rune >= kSmallBins) nbig++;
     }
-    size_t cap = 2;
-    while (cap < 2 * nbig) cap <<= 1;
-    pl.btab.assign(cap, CodeEntry{0xFFFFFFFFu, 0, 0});
-    for (const HuffCode &cd : codes) {
-        if (cd.rune < kSmallBins) continue;
-        uint32_t h = big_hash((uint32_t)cd.rune) & (uint32_t)(cap - 1);
-        while (pl.btab[h].rune != 0xFFFFFFFFu) h = (h + 1) & (uint32_t)(cap - 1);
-        pl.btab[h] = CodeEntry{(uint32_t)cd.rune, cd.len, cd.code};
-    }
+    while (pl.btab_cap < 2 * nbig) pl.btab_cap <<= 1;
     pl.pad = (uint32_t)((8 - pl.total_bits % 8) % 8);  // huffman.go:245-249
     pl.prefix.push_back(0x5C);
     pl.prefix.push_back(0x0A);
@@ -594,6 +615,7 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     out.rc = in.rc;
     if (G == 0) return RSN_OK;
     ArenaScope scope(s);
+    Trace tr("hc batch", s);
     size_t cap = 1;
     for (size_t f = 0; f < G; f++) {
         if (in.rc[f] != RSN_OK) continue;
@@ -631,6 +653,7 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     RSN_CUDA(cudaMemcpyAsync(h_hist.data(), hist.p, G * kHistStride * 4, cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HencFile), cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaStreamSynchronize(s));
+    tr.mark("hist");
     std::vector<std::vector<uint32_t>> h_big(G);
     for (size_t f = 0; f < G; f++) {
         if (!h[f].big_n) continue;
@@ -639,22 +662,24 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
                                  cudaMemcpyDeviceToHost, s));
     }
     RSN_CUDA(cudaStreamSynchronize(s));
+    tr.mark("big lists d2h");
     // ---- host: tree, codes, header per file (exactly as the reference builds them)
     std::vector<HencHost> plan(G);
-    parallel_for(G, 8, [&](size_t f) {
+    parallel_for(G, batch_host_threads(), [&](size_t f) {
         if (out.rc[f] != RSN_OK) {
             plan[f].rc = out.rc[f];
             return;
         }
         henc_host_plan(h_hist.data() + f * kHistStride, h_big[f], plan[f]);
     });
+    tr.mark("host trees");
     // ---- tables and prefixes of all files in one upload; one result buffer
-    std::vector<uint8_t> tab;
+    static thread_local std::vector<uint8_t> tab;  // keeps its pages between groups
     std::vector<size_t> o_code(G), o_len(G), o_btab(G), o_pre(G);
-    auto put = [&](const void *src, size_t bytes) {
-        const size_t at = (tab.size() + 15) & ~(size_t)15;
-        tab.resize(at + bytes);
-        memcpy(tab.data() + at, src, bytes);
+    size_t tab_n = 0;
+    auto room = [&](size_t bytes) {
+        const size_t at = (tab_n + 15) & ~(size_t)15;
+        tab_n = at + bytes;
         return at;
     };
     size_t total = 0;
@@ -663,17 +688,27 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     for (size_t f = 0; f < G; f++) {
         out.rc[f] = plan[f].rc;
         if (plan[f].rc != RSN_OK) continue;
-        o_code[f] = put(plan[f].scode.data(), kSmallBins * 8);
-        o_len[f] = put(plan[f].slen.data(), kSmallBins);
-        o_btab[f] = put(plan[f].btab.data(), plan[f].btab.size() * sizeof(CodeEntry));
-        o_pre[f] = put(plan[f].prefix.data(), plan[f].prefix.size());
+        o_code[f] = room(kSmallBins * 8);
+        o_len[f] = room(kSmallBins);
+        o_btab[f] = room(plan[f].btab_cap * sizeof(CodeEntry));
+        o_pre[f] = room(plan[f].prefix.size());
         out_base[f] = total;
         total += (plan[f].total + 16 + 255) & ~(size_t)255;
         (plan[f].maxlen <= 24 ? any_packed : any_wide) = true;
     }
+    if (tab.size() < tab_n) tab.resize(tab_n);
+    uint8_t *const tabp = tab.data();  // (a thread_local name inside the lambda would be the helper thread's own)
+    parallel_for(G, batch_host_threads(), [&, tabp](size_t f) {
+        if (plan[f].rc != RSN_OK) return;
+        henc_fill_tables(plan[f], reinterpret_cast<uint64_t *>(tabp + o_code[f]), tabp + o_len[f],
+                         reinterpret_cast<CodeEntry *>(tabp + o_btab[f]));
+        memcpy(tabp + o_pre[f], plan[f].prefix.data(), plan[f].prefix.size());
+    });
+    tr.mark("tables: host concat");
     DevBuf dtab, res;
-    RSN_TRY(dtab.alloc(tab.size() + 256, s));
+    RSN_TRY(dtab.alloc(tab_n + 256, s));
     RSN_TRY(res.alloc_out(total + 256, s));
+    tr.mark("tables: alloc");
     for (size_t f = 0; f < G; f++) {
         HencFile &r = h[f];
         if (plan[f].rc != RSN_OK) {
@@ -684,15 +719,16 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
         r.scode = reinterpret_cast<const uint64_t *>(dtab.as<uint8_t>() + o_code[f]);
         r.slen = dtab.as<uint8_t>() + o_len[f];
         r.btab = reinterpret_cast<const CodeEntry *>(dtab.as<uint8_t>() + o_btab[f]);
-        r.bmask = (uint32_t)(plan[f].btab.size() - 1);
+        r.bmask = (uint32_t)(plan[f].btab_cap - 1);
         r.out_words = reinterpret_cast<uint32_t *>(res.as<uint8_t>() + out_base[f]);
         r.bit_base = (uint64_t)plan[f].prefix.size() * 8 + plan[f].pad;
         r.prefix = dtab.as<uint8_t>() + o_pre[f];
         r.prefix_n = plan[f].prefix.size();
     }
-    if (!tab.empty()) RSN_CUDA(cudaMemcpyAsync(dtab.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, s));
+    if (tab_n) RSN_CUDA(cudaMemcpyAsync(dtab.p, tabp, tab_n, cudaMemcpyHostToDevice, s));
     RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HencFile), cudaMemcpyHostToDevice, s));
     RSN_CUDA(cudaMemsetAsync(res.p, 0, total + 256, s));
+    tr.mark("tables");
     // ---- phase 2: code-length scan and bit pack
     const dim3 tgrid((unsigned)tiles_cap, g);
     RSN_LAUNCH(kb_enc_prefix, g, 256, 0, s, b);
@@ -701,6 +737,7 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     if (any_packed) RSN_LAUNCH(kb_enc_write<true>, tgrid, kTileThreads, 0, s, b);
     if (any_wide) RSN_LAUNCH(kb_enc_write<false>, tgrid, kTileThreads, 0, s, b);
     RSN_CUDA(cudaStreamSynchronize(s));  // tab / h are read by the copies above
+    tr.mark("encode");
     for (size_t f = 0; f < G; f++) {
         if (out.rc[f] != RSN_OK) continue;
         out.ptr[f] = res.as<uint8_t>() + out_base[f];

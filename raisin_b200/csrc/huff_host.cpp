@@ -47,24 +47,31 @@ struct GoHeapT {
     std::vector<E> h;
     Less lt;
     bool less(int i, int j) const { return lt(h[i], h[j]); }
+    // Go's up/down swap the moving element with a parent/child at every level; carrying it in a
+    // register and writing it once at the end leaves the array in exactly the same state.
     void up(int j) {
+        const E v = h[j];
         for (;;) {
             int i = (j - 1) / 2;  // parent; truncating division keeps j == 0 at 0
-            if (i == j || !less(j, i)) break;
-            std::swap(h[i], h[j]);
+            if (i == j || !lt(v, h[i])) break;
+            h[j] = h[i];
             j = i;
         }
+        h[j] = v;
     }
     void down(int i, int n) {
+        const E v = h[i];
         for (;;) {
             int j1 = 2 * i + 1;
             if (j1 >= n || j1 < 0) break;
-            int j = j1;
-            if (j1 + 1 < n && less(j1 + 1, j1)) j = j1 + 1;
-            if (!less(j, i)) break;
-            std::swap(h[i], h[j]);
+            // which child is smaller is a coin flip: select without a branch
+            const int j2 = j1 + 1 < n ? j1 + 1 : j1;
+            const int j = lt(h[j2], h[j1]) ? j2 : j1;
+            if (!lt(h[j], v)) break;
+            h[i] = h[j];
             i = j;
         }
+        h[i] = v;
     }
     void init() {
         int n = (int)h.size();
@@ -245,17 +252,11 @@ static int64_t atoi_digits(const std::vector<uint8_t> &d) {
 }
 
 bool huff_parse_header(const uint8_t *h, size_t hn, std::vector<HuffLeaf> &leaves) {
-    // rune -> (freq, seen) with map semantics (the last assignment wins); a dense table beats a hash
-    // map by far when the header has ~1e5 records (binary input)
-    std::vector<int64_t> dense;
-    std::vector<uint8_t> seen;
-    std::unordered_map<int32_t, int64_t> m;
-    const bool use_dense = hn > 8192;
-    if (use_dense) {
-        dense.assign(0x110000, 0);
-        seen.assign(0x110000, 0);
-    }
-    std::vector<int32_t> order;
+    // rune -> freq with map semantics (the last assignment wins).  Records are collected in order
+    // and de-duplicated afterwards: through a dense table over the rune space when the header is
+    // huge (~1e5 records, binary input), else by sorting (rune, sequence number) keys — touching
+    // 10 MB of table per call would dominate small files.
+    std::vector<HuffLeaf> rec;
     std::vector<uint8_t> temp;
     for (size_t i = 0; i < hn; i++) {
         if (h[i] != '|') {
@@ -279,21 +280,24 @@ bool huff_parse_header(const uint8_t *h, size_t hn, std::vector<HuffLeaf> &leave
             const uint8_t b1 = p + 1 < hn ? h[p + 1] : 0, b2 = p + 2 < hn ? h[p + 2] : 0, b3 = p + 3 < hn ? h[p + 3] : 0;
             utf8_decode_at(h[p], b1, b2, b3, hn - p, &sym);
         }
-        if (use_dense) {
-            if (!seen[sym]) {
-                seen[sym] = 1;
-                order.push_back(sym);
-            }
-            dense[sym] = f;
-        } else {
-            if (m.find(sym) == m.end()) order.push_back(sym);
-            m[sym] = f;
-        }
+        rec.push_back(HuffLeaf{f, sym});
         i++;
     }
     leaves.clear();
-    leaves.reserve(order.size());
-    for (int32_t r : order) leaves.push_back(HuffLeaf{use_dense ? dense[r] : m[r], r});
+    const size_t k = rec.size();
+    if (k > ((size_t)1 << 16)) {
+        std::vector<uint32_t> last(0x110000, 0);  // 1 + index of the last record of the rune
+        for (size_t i = 0; i < k; i++) last[rec[i].rune] = (uint32_t)i + 1;
+        for (size_t i = 0; i < k; i++)
+            if (last[rec[i].rune] == (uint32_t)i + 1) leaves.push_back(rec[i]);
+        return true;
+    }
+    std::vector<uint64_t> keys(k);
+    for (size_t i = 0; i < k; i++) keys[i] = ((uint64_t)(uint32_t)rec[i].rune << 32) | (uint64_t)i;
+    std::sort(keys.begin(), keys.end());
+    leaves.reserve(k);
+    for (size_t i = 0; i < k; i++)
+        if (i + 1 == k || (keys[i + 1] >> 32) != (keys[i] >> 32)) leaves.push_back(rec[(size_t)(keys[i] & 0xFFFFFFFFu)]);
     return true;
 }
 
