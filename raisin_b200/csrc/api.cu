@@ -6,6 +6,7 @@
 #include "lzss.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -400,14 +401,19 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
     RSN_TRY(parse_layers(algorithms, algos));
     RSN_TRY(ensure_ctx());
     const int dev = ctx().device;
-    if (workers <= 0) workers = 6;
+    if (workers <= 0) workers = 8;
     std::vector<int> rc_local;
     if (!rcs) {
         rc_local.assign(count ? count : 1, RSN_OK);
         rcs = rc_local.data();
     }
     // groups of small files
-    constexpr size_t kGroupBytes = (size_t)16 << 20, kGroupFiles = 512;
+    size_t kGroupBytes = (size_t)16 << 20;
+    constexpr size_t kGroupFiles = 512;
+    if (const char *e = getenv("RSN_BATCH_GROUP_MIB")) {  // tuning knob
+        const long v = atol(e);
+        if (v >= 1 && v <= 1024) kGroupBytes = (size_t)v << 20;
+    }
     std::vector<std::vector<size_t>> groups;
     std::vector<size_t> singles;
     if (!device) {

@@ -453,26 +453,11 @@ __global__ void kb_hdec_write(HdecFile *__restrict__ files, const uint64_t *__re
 namespace {
 struct HdecHost {           // what the host learns about one file before any kernel runs
     int rc = RSN_OK;
-    bool per_file = false;  // leave it to huff_decompress_dev (single-leaf trees)
+    bool per_file = false;  // leave it to huff_decompress_dev (single-leaf trees, huge frequencies)
     size_t pay_off = 0;
     uint64_t diff = 0, max = 0;
-    HuffTree tree;
+    std::vector<uint32_t> freq, rune;  // leaves in (freq asc, rune asc) order
 };
-
-// lookup table over the first kLutBits bits of a code, written into the group's staging buffer
-void hdec_fill_lut(const HuffTree &tree, uint32_t *lut) {
-    for (uint32_t idx = 0; idx < (1u << kLutBits); idx++) {
-        int32_t node = tree.root;
-        uint32_t len = 0;
-        while (tree.nodes[node].left >= 0 && len < (uint32_t)kLutBits) {
-            const uint32_t bit = (idx >> (kLutBits - 1 - len)) & 1u;
-            node = bit ? tree.nodes[node].right : tree.nodes[node].left;
-            len++;
-        }
-        if (tree.nodes[node].left < 0) lut[idx] = (1u << 31) | (len << 21) | ((uint32_t)tree.nodes[node].right & 0x1FFFFFu);
-        else lut[idx] = (uint32_t)node;
-    }
-}
 
 void hdec_host_plan(const uint8_t *h, size_t n, HdecHost &pl) {
     ptrdiff_t sp = -1;
@@ -490,7 +475,6 @@ void hdec_host_plan(const uint8_t *h, size_t n, HdecHost &pl) {
         pl.rc = RSN_ERR_BAD_HEADER;
         return;
     }
-    huff_build_tree(leaves, pl.tree);
     pl.pay_off = (size_t)sp + 2;
     const size_t pn = n - pl.pay_off;
     pl.diff = pn ? h[pl.pay_off] : 0;
@@ -500,14 +484,28 @@ void hdec_host_plan(const uint8_t *h, size_t n, HdecHost &pl) {
         return;
     }
     pl.max = nbits - pl.diff;
-    const HuffTree &tree = pl.tree;
-    if (tree.nodes[tree.root].left < 0) {
+    // the device builder packs (frequency sum, node) into one word: anything a header could say
+    // beyond that, and the single-leaf special cases, go through the single-stream call
+    uint64_t sum = 0;
+    bool fits = leaves.size() >= 2 && leaves.size() <= kTreeMaxLeaves;
+    for (const HuffLeaf &l : leaves) {
+        if (l.freq < 0 || l.freq >= ((int64_t)1 << 32)) fits = false;
+        else sum += (uint64_t)l.freq;
+    }
+    if (!fits || sum >= ((uint64_t)1 << 39)) {
         pl.per_file = true;
         return;
     }
     if (pl.max == 0) {
-        pl.rc = RSN_ERR_TRUNCATED;
+        pl.rc = RSN_ERR_TRUNCATED;  // data[0] on an empty bit string
         return;
+    }
+    huff_sort_leaves(leaves);
+    pl.freq.resize(leaves.size());
+    pl.rune.resize(leaves.size());
+    for (size_t i = 0; i < leaves.size(); i++) {
+        pl.freq[i] = (uint32_t)leaves[i].freq;
+        pl.rune[i] = (uint32_t)leaves[i].rune;
     }
 }
 }  // namespace
@@ -528,36 +526,46 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         }
         hdec_host_plan(h_in[f], (size_t)in.n[f], plan[f]);
     });
-    tr.mark("host headers+trees");
-    // tables of all files in one upload: [nodes | lut] per file
+    tr.mark("host headers");
+    // leaves of all files in one upload; trees and 12-bit tables on the device (huff_tree.cu)
     std::vector<HdecFile> h(G);
     static thread_local std::vector<uint8_t> tab;  // keeps its pages between groups
-    std::vector<size_t> tab_off(G, 0);
-    size_t tab_n = 0;
-    const size_t lb = ((size_t)1 << kLutBits) * 4;
+    std::vector<size_t> o_freq(G, 0), o_rune(G, 0), o_nodes(G, 0), o_parent(G, 0), o_lut(G, 0);
+    size_t tab_n = 0, scr_n = 0;
+    auto room = [](size_t &cursor, size_t bytes) {
+        const size_t at = (cursor + 15) & ~(size_t)15;
+        cursor = at + bytes;
+        return at;
+    };
     size_t subs_total = 0, subs_cap = 1;
+    uint32_t kmax = 1;
     for (size_t f = 0; f < G; f++) {
         h[f] = HdecFile{};
         out.rc[f] = plan[f].rc;
         if (plan[f].rc != RSN_OK || plan[f].per_file) continue;
-        tab_off[f] = tab_n;
-        const size_t nb = plan[f].tree.nodes.size() * sizeof(HuffNode);
-        tab_n += (nb + lb + 255) & ~(size_t)255;
+        const size_t k = plan[f].freq.size();
+        kmax = std::max<uint32_t>(kmax, (uint32_t)k);
+        o_freq[f] = room(tab_n, k * 4);
+        o_rune[f] = room(tab_n, k * 4);
+        o_nodes[f] = room(scr_n, 2 * k * sizeof(HuffNodeDev));
+        o_parent[f] = room(scr_n, 2 * k * 4);
+        o_lut[f] = room(scr_n, ((size_t)1 << kLutBits) * 4);
         h[f].subs = div_up(plan[f].max, kSubBits);
         h[f].sub_base = subs_total;
         subs_total += h[f].subs;
         subs_cap = std::max<size_t>(subs_cap, h[f].subs);
     }
     if (tab.size() < tab_n) tab.resize(tab_n);
-    uint8_t *const tabp = tab.data();  // (a thread_local name inside the lambda would be the helper thread's own)
-    parallel_for(G, batch_host_threads(), [&, tabp](size_t f) {
-        if (!h[f].subs) return;
-        const size_t nb = plan[f].tree.nodes.size() * sizeof(HuffNode);
-        memcpy(tabp + tab_off[f], plan[f].tree.nodes.data(), nb);
-        hdec_fill_lut(plan[f].tree, reinterpret_cast<uint32_t *>(tabp + tab_off[f] + nb));
-    });
-    DevBuf dtab, files, start, endA, endB, cnt, off, flag;
+    uint8_t *const tabp = tab.data();
+    for (size_t f = 0; f < G; f++) {
+        if (!h[f].subs) continue;
+        memcpy(tabp + o_freq[f], plan[f].freq.data(), plan[f].freq.size() * 4);
+        memcpy(tabp + o_rune[f], plan[f].rune.data(), plan[f].rune.size() * 4);
+    }
+    DevBuf dtab, dscr, djobs, files, start, endA, endB, cnt, off, flag;
     RSN_TRY(dtab.alloc(tab_n + 256, s));
+    RSN_TRY(dscr.alloc(scr_n + 256, s));
+    RSN_TRY(djobs.alloc(G * sizeof(TreeJob), s));
     RSN_TRY(files.alloc(G * sizeof(HdecFile), s));
     RSN_TRY(start.alloc(subs_total * 8 + 8, s));
     RSN_TRY(endA.alloc(subs_total * 8 + 8, s));
@@ -565,8 +573,17 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
     RSN_TRY(cnt.alloc(subs_total * 8 + 8, s));
     RSN_TRY(off.alloc(subs_total * 8 + 8, s));
     RSN_TRY(flag.alloc(16, s));
+    std::vector<TreeJob> jobs(G);
     for (size_t f = 0; f < G; f++) {
+        jobs[f] = TreeJob{};
         if (!h[f].subs) continue;
+        TreeJob &j = jobs[f];
+        j.freq = reinterpret_cast<const uint32_t *>(dtab.as<uint8_t>() + o_freq[f]);
+        j.rune = reinterpret_cast<const uint32_t *>(dtab.as<uint8_t>() + o_rune[f]);
+        j.k = (uint32_t)plan[f].freq.size();
+        j.nodes = reinterpret_cast<HuffNodeDev *>(dscr.as<uint8_t>() + o_nodes[f]);
+        j.parent = reinterpret_cast<uint32_t *>(dscr.as<uint8_t>() + o_parent[f]);
+        j.lut = reinterpret_cast<uint32_t *>(dscr.as<uint8_t>() + o_lut[f]);
         DecParams &p = h[f].p;
         const size_t pn = (size_t)in.n[f] - plan[f].pay_off;
         const uintptr_t addr = reinterpret_cast<uintptr_t>(in.ptr[f] + plan[f].pay_off + 1);
@@ -574,12 +591,13 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         p.bit0 = (uint64_t)(addr & 3) * 8 + plan[f].diff;
         p.nwords = ((addr & 3) + (pn - 1) + 3) / 4;
         p.max = plan[f].max;
-        const size_t nb = plan[f].tree.nodes.size() * sizeof(HuffNode);
-        p.nodes = reinterpret_cast<const HuffNode *>(dtab.as<uint8_t>() + tab_off[f]);
-        p.lut = reinterpret_cast<const uint32_t *>(dtab.as<uint8_t>() + tab_off[f] + nb);
-        p.root = plan[f].tree.root;
+        p.nodes = reinterpret_cast<const HuffNode *>(j.nodes);
+        p.lut = j.lut;
+        p.root = 0;  // (the decode kernels start from the table, not from the root)
     }
     if (tab_n) RSN_CUDA(cudaMemcpyAsync(dtab.p, tabp, tab_n, cudaMemcpyHostToDevice, s));
+    RSN_CUDA(cudaMemcpyAsync(djobs.p, jobs.data(), G * sizeof(TreeJob), cudaMemcpyHostToDevice, s));
+    if (subs_total) RSN_TRY(huff_tree_batch(djobs.as<TreeJob>(), G, kmax, s));
     RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HdecFile), cudaMemcpyHostToDevice, s));
     const dim3 grid((unsigned)div_up(subs_cap, 128), (unsigned)G);
     Ctx &c = ctx();

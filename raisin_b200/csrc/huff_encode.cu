@@ -123,12 +123,6 @@ __global__ void k_hist_compact(const unsigned long long *__restrict__ hist, Rune
 
 // ============================================================================= K10 encode
 
-struct CodeEntry {
-    uint32_t rune;
-    uint32_t len;
-    uint64_t code;
-};
-
 // Codes of runes >= 256: a dense table over the rune space (single stream), or a small
 // open-addressing table per file (batches; every rune looked up is present).
 struct DenseBig {
@@ -433,10 +427,11 @@ struct HencFile {
     const uint64_t *scode;  // codes / lengths of runes < 256
     const uint8_t *slen;
     const CodeEntry *btab;  // hash table of the other runes
-    uint32_t bmask, pad;
+    uint32_t bmask;
+    uint32_t pad;         // zero bits in front of the first payload byte
     uint32_t *out_words;  // 4-byte aligned start of the file's output
     uint64_t bit_base;    // first code bit: 8 * (header + 5C 0A + pad byte) + pad
-    const uint8_t *prefix;
+    const uint8_t *prefix;  // header | 5C 0A
     uint64_t prefix_n;
 };
 
@@ -495,6 +490,7 @@ __global__ void __launch_bounds__(256) kb_enc_prefix(HencBatch b) {
     const HencFile &f = b.files[blockIdx.x];
     uint8_t *dst = reinterpret_cast<uint8_t *>(f.out_words);
     for (uint64_t i = threadIdx.x; i < f.prefix_n; i += blockDim.x) dst[i] = f.prefix[i];
+    if (threadIdx.x == 0 && f.prefix_n) dst[f.prefix_n] = (uint8_t)f.pad;  // huffman.go:250
 }
 
 __global__ void __launch_bounds__(kTileThreads) kb_enc_count(HencBatch b) {
@@ -521,32 +517,11 @@ __global__ void __launch_bounds__(kTileThreads) kb_enc_write(HencBatch b) {
 namespace {
 struct HencHost {
     int rc = RSN_OK;
-    std::vector<uint8_t> prefix;      // header | 5C 0A | pad byte
-    std::vector<HuffCode> codes;
+    bool per_file = false;            // alphabet too large for the device tree builder
+    std::vector<uint8_t> prefix;      // header | 5C 0A (the pad byte follows once the bit count is known)
+    std::vector<uint32_t> freq, rune; // leaves in (freq asc, rune asc) order
     size_t btab_cap = 2;              // power-of-two hash table size for the runes >= 256
-    uint64_t total_bits = 0, total = 0;
-    uint32_t pad = 0, maxlen = 0;
 };
-
-// the file's device tables, written straight into the group's staging buffer
-void henc_fill_tables(const HencHost &pl, uint64_t *scode, uint8_t *slen, CodeEntry *btab) {
-    for (int i = 0; i < kSmallBins; i++) {
-        scode[i] = 0;
-        slen[i] = 0;
-    }
-    for (size_t i = 0; i < pl.btab_cap; i++) btab[i] = CodeEntry{0xFFFFFFFFu, 0, 0};  // empty
-    const uint32_t mask = (uint32_t)(pl.btab_cap - 1);
-    for (const HuffCode &cd : pl.codes) {
-        if (cd.rune < kSmallBins) {
-            scode[cd.rune] = cd.code;
-            slen[cd.rune] = cd.len;
-            continue;
-        }
-        uint32_t h = big_hash((uint32_t)cd.rune) & mask;
-        while (btab[h].rune != 0xFFFFFFFFu) h = (h + 1) & mask;
-        btab[h] = CodeEntry{(uint32_t)cd.rune, cd.len, cd.code};
-    }
-}
 
 // runes are below 2^21: three byte-wise counting passes
 void sort_runes(std::vector<uint32_t> &v) {
@@ -566,46 +541,43 @@ void sort_runes(std::vector<uint32_t> &v) {
     if (src != v.data()) std::copy(src, src + v.size(), v.data());
 }
 
+// histogram -> leaves in the reference's order, header bytes (huffman.go:312-318)
 void henc_host_plan(const uint32_t *hist, std::vector<uint32_t> &big, HencHost &pl) {
     std::vector<HuffLeaf> leaves;
     for (int r = 0; r < kSmallBins; r++)
         if (hist[r]) leaves.push_back(HuffLeaf{(int64_t)hist[r], r});
     sort_runes(big);
-    bool fffd_done = hist[256] == 0;
+    size_t nbig = 0;
     for (size_t i = 0; i < big.size();) {
         size_t j = i;
         while (j < big.size() && big[j] == big[i]) j++;
-        if (!fffd_done && big[i] > 0xFFFDu) {
-            leaves.push_back(HuffLeaf{(int64_t)hist[256], 0xFFFD});
-            fffd_done = true;
-        }
         leaves.push_back(HuffLeaf{(int64_t)(j - i), (int32_t)big[i]});
+        nbig++;
         i = j;
     }
-    if (!fffd_done) leaves.push_back(HuffLeaf{(int64_t)hist[256], 0xFFFD});
+    if (hist[256]) {
+        leaves.push_back(HuffLeaf{(int64_t)hist[256], 0xFFFD});
+        nbig++;
+    }
     if (leaves.empty()) {
         pl.rc = RSN_ERR_EMPTY_INPUT;
         return;
     }
-    HuffTree tree;
-    huff_build_tree(leaves, tree);
-    if (!huff_codes(tree, pl.codes)) {
-        pl.rc = RSN_ERR_UNSUPPORTED;  // a code longer than 64 bits
+    if (leaves.size() > kTreeMaxLeaves) {
+        pl.per_file = true;
         return;
     }
     huff_header(leaves, pl.prefix);
-    size_t nbig = 0;
-    for (const HuffCode &cd : pl.codes) {
-        pl.total_bits += (uint64_t)cd.len * (uint64_t)cd.freq;
-        pl.maxlen = std::max<uint32_t>(pl.maxlen, cd.len);
-        if (cd.rune >= kSmallBins) nbig++;
-    }
-    while (pl.btab_cap < 2 * nbig) pl.btab_cap <<= 1;
-    pl.pad = (uint32_t)((8 - pl.total_bits % 8) % 8);  // huffman.go:245-249
     pl.prefix.push_back(0x5C);
     pl.prefix.push_back(0x0A);
-    pl.prefix.push_back((uint8_t)pl.pad);
-    pl.total = pl.prefix.size() + (pl.total_bits + pl.pad) / 8;
+    huff_sort_leaves(leaves);
+    pl.freq.resize(leaves.size());
+    pl.rune.resize(leaves.size());
+    for (size_t i = 0; i < leaves.size(); i++) {
+        pl.freq[i] = (uint32_t)leaves[i].freq;
+        pl.rune[i] = (uint32_t)leaves[i].rune;
+    }
+    while (pl.btab_cap < 2 * nbig) pl.btab_cap <<= 1;
 }
 }  // namespace
 
@@ -663,7 +635,8 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     }
     RSN_CUDA(cudaStreamSynchronize(s));
     tr.mark("big lists d2h");
-    // ---- host: tree, codes, header per file (exactly as the reference builds them)
+    // ---- host: leaves in the reference's order and header bytes per file; trees and codes on the
+    // device, one warp per file (huff_tree.cu)
     std::vector<HencHost> plan(G);
     parallel_for(G, batch_host_threads(), [&](size_t f) {
         if (out.rc[f] != RSN_OK) {
@@ -672,60 +645,101 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
         }
         henc_host_plan(h_hist.data() + f * kHistStride, h_big[f], plan[f]);
     });
-    tr.mark("host trees");
-    // ---- tables and prefixes of all files in one upload; one result buffer
-    static thread_local std::vector<uint8_t> tab;  // keeps its pages between groups
-    std::vector<size_t> o_code(G), o_len(G), o_btab(G), o_pre(G);
-    size_t tab_n = 0;
-    auto room = [&](size_t bytes) {
-        const size_t at = (tab_n + 15) & ~(size_t)15;
-        tab_n = at + bytes;
+    tr.mark("host leaves+headers");
+    static thread_local std::vector<uint8_t> tab;  // staging: keeps its pages between groups
+    std::vector<size_t> o_freq(G), o_rune(G), o_pre(G), o_small(G), o_btab(G), o_nodes(G), o_parent(G);
+    size_t tab_n = 0, zero_n = 0, ff_n = 0, scr_n = 0;
+    auto room = [](size_t &cursor, size_t bytes) {
+        const size_t at = (cursor + 15) & ~(size_t)15;
+        cursor = at + bytes;
         return at;
     };
-    size_t total = 0;
-    std::vector<size_t> out_base(G, 0);
-    bool any_packed = false, any_wide = false;
+    uint32_t kmax = 1;
     for (size_t f = 0; f < G; f++) {
         out.rc[f] = plan[f].rc;
-        if (plan[f].rc != RSN_OK) continue;
-        o_code[f] = room(kSmallBins * 8);
-        o_len[f] = room(kSmallBins);
-        o_btab[f] = room(plan[f].btab_cap * sizeof(CodeEntry));
-        o_pre[f] = room(plan[f].prefix.size());
-        out_base[f] = total;
-        total += (plan[f].total + 16 + 255) & ~(size_t)255;
-        (plan[f].maxlen <= 24 ? any_packed : any_wide) = true;
+        if (plan[f].rc != RSN_OK || plan[f].per_file) continue;
+        const size_t k = plan[f].freq.size();
+        kmax = std::max<uint32_t>(kmax, (uint32_t)k);
+        o_freq[f] = room(tab_n, k * 4);
+        o_rune[f] = room(tab_n, k * 4);
+        o_pre[f] = room(tab_n, plan[f].prefix.size());
+        o_small[f] = room(zero_n, kSmallBins * 8 + kSmallBins);
+        o_btab[f] = room(ff_n, plan[f].btab_cap * sizeof(CodeEntry));
+        o_nodes[f] = room(scr_n, (2 * k) * sizeof(HuffNodeDev));
+        o_parent[f] = room(scr_n, (2 * k) * 4);
     }
     if (tab.size() < tab_n) tab.resize(tab_n);
     uint8_t *const tabp = tab.data();  // (a thread_local name inside the lambda would be the helper thread's own)
     parallel_for(G, batch_host_threads(), [&, tabp](size_t f) {
-        if (plan[f].rc != RSN_OK) return;
-        henc_fill_tables(plan[f], reinterpret_cast<uint64_t *>(tabp + o_code[f]), tabp + o_len[f],
-                         reinterpret_cast<CodeEntry *>(tabp + o_btab[f]));
+        if (plan[f].rc != RSN_OK || plan[f].per_file) return;
+        memcpy(tabp + o_freq[f], plan[f].freq.data(), plan[f].freq.size() * 4);
+        memcpy(tabp + o_rune[f], plan[f].rune.data(), plan[f].rune.size() * 4);
         memcpy(tabp + o_pre[f], plan[f].prefix.data(), plan[f].prefix.size());
     });
-    tr.mark("tables: host concat");
-    DevBuf dtab, res;
+    DevBuf dtab, dzero, dff, dscr, djobs;
     RSN_TRY(dtab.alloc(tab_n + 256, s));
-    RSN_TRY(res.alloc_out(total + 256, s));
-    tr.mark("tables: alloc");
+    RSN_TRY(dzero.alloc(zero_n + 256, s));
+    RSN_TRY(dff.alloc(ff_n + 256, s));
+    RSN_TRY(dscr.alloc(scr_n + 256, s));
+    RSN_TRY(djobs.alloc(G * sizeof(TreeJob), s));
+    std::vector<TreeJob> jobs(G);
+    for (size_t f = 0; f < G; f++) {
+        TreeJob &j = jobs[f];
+        j = TreeJob{};
+        if (plan[f].rc != RSN_OK || plan[f].per_file) continue;
+        j.freq = reinterpret_cast<const uint32_t *>(dtab.as<uint8_t>() + o_freq[f]);
+        j.rune = reinterpret_cast<const uint32_t *>(dtab.as<uint8_t>() + o_rune[f]);
+        j.k = (uint32_t)plan[f].freq.size();
+        j.bmask = (uint32_t)(plan[f].btab_cap - 1);
+        j.nodes = reinterpret_cast<HuffNodeDev *>(dscr.as<uint8_t>() + o_nodes[f]);
+        j.parent = reinterpret_cast<uint32_t *>(dscr.as<uint8_t>() + o_parent[f]);
+        j.scode = reinterpret_cast<uint64_t *>(dzero.as<uint8_t>() + o_small[f]);
+        j.slen = dzero.as<uint8_t>() + o_small[f] + kSmallBins * 8;
+        j.btab = reinterpret_cast<CodeEntry *>(dff.as<uint8_t>() + o_btab[f]);
+    }
+    if (tab_n) RSN_CUDA(cudaMemcpyAsync(dtab.p, tabp, tab_n, cudaMemcpyHostToDevice, s));
+    RSN_CUDA(cudaMemcpyAsync(djobs.p, jobs.data(), G * sizeof(TreeJob), cudaMemcpyHostToDevice, s));
+    RSN_CUDA(cudaMemsetAsync(dzero.p, 0, zero_n + 256, s));
+    RSN_CUDA(cudaMemsetAsync(dff.p, 0xFF, ff_n + 256, s));
+    RSN_TRY(huff_tree_batch(djobs.as<TreeJob>(), G, kmax, s));
+    RSN_CUDA(cudaMemcpyAsync(jobs.data(), djobs.p, G * sizeof(TreeJob), cudaMemcpyDeviceToHost, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    tr.mark("device trees");
+    // ---- sizes, one result buffer
+    size_t total = 0;
+    std::vector<size_t> out_base(G, 0), out_total(G, 0);
+    bool any_packed = false, any_wide = false;
     for (size_t f = 0; f < G; f++) {
         HencFile &r = h[f];
-        if (plan[f].rc != RSN_OK) {
+        if (plan[f].rc != RSN_OK || plan[f].per_file) {
             r.n = 0;
             continue;
         }
-        r.packed = plan[f].maxlen <= 24;
-        r.scode = reinterpret_cast<const uint64_t *>(dtab.as<uint8_t>() + o_code[f]);
-        r.slen = dtab.as<uint8_t>() + o_len[f];
-        r.btab = reinterpret_cast<const CodeEntry *>(dtab.as<uint8_t>() + o_btab[f]);
-        r.bmask = (uint32_t)(plan[f].btab_cap - 1);
-        r.out_words = reinterpret_cast<uint32_t *>(res.as<uint8_t>() + out_base[f]);
-        r.bit_base = (uint64_t)plan[f].prefix.size() * 8 + plan[f].pad;
+        const TreeJob &j = jobs[f];
+        if (j.flags & 1u) {  // a code longer than 64 bits
+            out.rc[f] = RSN_ERR_UNSUPPORTED;
+            r.n = 0;
+            continue;
+        }
+        const uint32_t pad = (uint32_t)((8 - j.total_bits % 8) % 8);  // huffman.go:245-249
+        out_total[f] = plan[f].prefix.size() + 1 + (size_t)((j.total_bits + pad) / 8);
+        out_base[f] = total;
+        total += (out_total[f] + 16 + 255) & ~(size_t)255;
+        r.packed = j.maxlen <= 24;
+        (r.packed ? any_packed : any_wide) = true;
+        r.scode = j.scode;
+        r.slen = j.slen;
+        r.btab = j.btab;
+        r.bmask = j.bmask;
+        r.pad = pad;
+        r.bit_base = (uint64_t)(plan[f].prefix.size() + 1) * 8 + pad;
         r.prefix = dtab.as<uint8_t>() + o_pre[f];
         r.prefix_n = plan[f].prefix.size();
     }
-    if (tab_n) RSN_CUDA(cudaMemcpyAsync(dtab.p, tabp, tab_n, cudaMemcpyHostToDevice, s));
+    DevBuf res;
+    RSN_TRY(res.alloc_out(total + 256, s));
+    for (size_t f = 0; f < G; f++)
+        if (h[f].n) h[f].out_words = reinterpret_cast<uint32_t *>(res.as<uint8_t>() + out_base[f]);
     RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HencFile), cudaMemcpyHostToDevice, s));
     RSN_CUDA(cudaMemsetAsync(res.p, 0, total + 256, s));
     tr.mark("tables");
@@ -736,14 +750,25 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     RSN_LAUNCH(kb_enc_finish, g, 256, 0, s, b);
     if (any_packed) RSN_LAUNCH(kb_enc_write<true>, tgrid, kTileThreads, 0, s, b);
     if (any_wide) RSN_LAUNCH(kb_enc_write<false>, tgrid, kTileThreads, 0, s, b);
-    RSN_CUDA(cudaStreamSynchronize(s));  // tab / h are read by the copies above
+    RSN_CUDA(cudaStreamSynchronize(s));  // h is read by the copy above
     tr.mark("encode");
     for (size_t f = 0; f < G; f++) {
-        if (out.rc[f] != RSN_OK) continue;
+        if (out.rc[f] != RSN_OK || plan[f].per_file) continue;
         out.ptr[f] = res.as<uint8_t>() + out_base[f];
-        out.n[f] = plan[f].total;
+        out.n[f] = out_total[f];
     }
     out.owned.push_back(res.release());
+    // alphabets beyond the device tree builder: the single-stream call
+    for (size_t f = 0; f < G; f++) {
+        if (out.rc[f] != RSN_OK || !plan[f].per_file) continue;
+        uint8_t *r = nullptr;
+        size_t rn = 0;
+        out.rc[f] = huff_compress_dev(in.ptr[f], (size_t)in.n[f], &r, &rn, s);
+        if (out.rc[f] != RSN_OK) continue;
+        out.ptr[f] = r;
+        out.n[f] = rn;
+        out.owned.push_back(r);
+    }
     return RSN_OK;
 }
 

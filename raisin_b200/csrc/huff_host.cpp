@@ -99,7 +99,7 @@ struct LessPacked {
 };
 }  // namespace
 
-void huff_build_tree(std::vector<HuffLeaf> leaves, HuffTree &t) {
+void huff_sort_leaves(std::vector<HuffLeaf> &leaves) {
     // leaves in (freq asc, rune asc) order (huffman.go:64-87)
     bool packable = true;
     for (const HuffLeaf &l : leaves)
@@ -114,6 +114,10 @@ void huff_build_tree(std::vector<HuffLeaf> leaves, HuffTree &t) {
             return a.freq != b.freq ? a.freq < b.freq : a.rune < b.rune;
         });
     }
+}
+
+void huff_build_tree(std::vector<HuffLeaf> leaves, HuffTree &t) {
+    huff_sort_leaves(leaves);
     const size_t k = leaves.size();
     t.nodes.clear();
     t.freq.clear();

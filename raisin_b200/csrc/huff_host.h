@@ -27,6 +27,8 @@ struct HuffTree {
 // buildTree (huffman.go:58-103): leaves ordered (freq asc, rune asc), container/heap Init,
 // then Pop,Pop,Push(a+b, left=a, right=b) until one node remains.  leaves must be non-empty.
 void huff_build_tree(std::vector<HuffLeaf> leaves, HuffTree &t);
+// the (freq asc, rune asc) leaf order alone (huffman.go:64-87)
+void huff_sort_leaves(std::vector<HuffLeaf> &leaves);
 
 struct HuffCode {
     int32_t rune;

@@ -22,6 +22,14 @@ n = len(files)
 total = sum(len(f) for f in files)
 keep = [rsn._lib._as_ptr(f) for f in files]
 ins = (C.c_void_p * n)(*[k[0] for k in keep])
+if os.environ.get("PROBE_PINNED"):  # inputs in pinned host memory instead of pageable Python bytes
+    lib.rsn_host_alloc.restype = C.c_void_p
+    pinned = []
+    for f in files:
+        p = lib.rsn_host_alloc(C.c_size_t(len(f)))
+        C.memmove(p, f, len(f))
+        pinned.append(p)
+    ins = (C.c_void_p * n)(*pinned)
 ns = (C.c_size_t * n)(*[k[1] for k in keep])
 for workers in (1, 2, 4, 6, 8, 12):
     best_c = best_d = 1e9
