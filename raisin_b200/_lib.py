@@ -130,6 +130,15 @@ def _as_ptr(data):
     return C.cast(C.c_char_p(b), C.c_void_p), len(b), b
 
 
+def bytes_at(ptr, n: int) -> bytes:
+    """Copy n bytes from a C pointer (ctypes.string_at takes a C int: results of 2 GiB and more
+    need the buffer route)."""
+    if n < (1 << 31) - 1:
+        return C.string_at(ptr, n)
+    addr = C.cast(ptr, C.c_void_p).value
+    return bytes((C.c_ubyte * n).from_address(addr))
+
+
 def call_host(fn, data, *extra) -> bytes:
     """Run a host-buffer entry point `fn(in, n, *extra, &out, &out_n)` and copy the result."""
     L = lib()
@@ -140,6 +149,6 @@ def call_host(fn, data, *extra) -> bytes:
     del keep
     check(rc)
     try:
-        return C.string_at(out, out_n.value)
+        return bytes_at(out, out_n.value)
     finally:
         L.rsn_free(out)

@@ -95,7 +95,7 @@ def batch(files, algorithms, compress_: bool = True, workers: int = 0):
         if rcs[i] != 0:
             res.append(None)
         else:
-            res.append(C.string_at(outs[i], out_ns[i]))
+            res.append(_lib.bytes_at(outs[i], out_ns[i]))
             L.rsn_free(outs[i])
     return res
 

@@ -35,11 +35,22 @@ def main():
     lib = rsn._lib.lib()
     rsn._lib.check(lib.rsn_init(local))
     n = int(mib * (1 << 20))
-    data = synth.repetitive(n, 5, motif=3000)  # highly repetitive, no bytes that need escaping
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
-    enc = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    # highly repetitive, no bytes that need escaping; large streams are tiled and mutated on the
+    # device (every rank builds the same bytes) so that no rank holds several host copies
+    base_n = min(n, 64 << 20)
+    base = torch.frombuffer(bytearray(synth.repetitive(base_n, 5, motif=3000)), dtype=torch.uint8).cuda()
+    if n > base_n:
+        enc = base.repeat(-(-n // base_n))[:n].contiguous()
+        idx = torch.arange(base_n, n, 65537, device="cuda")
+        enc[idx] = (97 + (idx // 65537) % 26).to(torch.uint8)   # one changed byte per ~64 KiB beyond the first tile
+        del idx
+    else:
+        enc = base
+    del base
+    torch.cuda.synchronize()
     W = 4096
 
     def match_fn(sl, window):
@@ -50,7 +61,8 @@ def main():
 
     times = []
     result = None
-    for it in range(4):
+    iters = int(os.environ.get("RSN_SHARD_ITERS", "4"))
+    for it in range(iters):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         if world > 1:
             dist.barrier()
@@ -61,7 +73,7 @@ def main():
         if rank == 0:
             out, on = C.c_void_p(), C.c_size_t()
             rsn._lib.check(lib.rsn_dev_lzss_emit(enc.data_ptr(), n, W, 0, packed.data_ptr(), C.byref(out), C.byref(on), sp))
-            if it == 3:
+            if it == iters - 1:
                 hb = (C.c_uint8 * on.value)()
                 rsn._lib.check(lib.rsn_dev_download(out, on.value, hb, sp))
                 result = bytes(hb)
@@ -79,8 +91,25 @@ def main():
                 "match_GBps": n / (m_ms * 1e-3) / 1e9, "compressed_bytes": len(result),
                 "allgather_bytes_per_rank": 4 * n}
         if check:
-            single = rsn.lz.CompressAsync(data)
+            # the whole compress on this GPU alone, device buffers, for the comparison and the timing
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            single = None
+            for it in range(2):
+                out, on = C.c_void_p(), C.c_size_t()
+                e0.record(stream)
+                rsn._lib.check(lib.rsn_dev_lzss_compress(enc.data_ptr(), n, W, 0, C.byref(out), C.byref(on), sp))
+                e1.record(stream)
+                torch.cuda.synchronize()
+                if it:
+                    hb = (C.c_uint8 * on.value)()
+                    rsn._lib.check(lib.rsn_dev_download(out, on.value, hb, sp))
+                    single = bytes(hb)
+                lib.rsn_dev_free(out, sp)
+            line["single_gpu_compress_ms"] = e0.elapsed_time(e1)
             line["identical_to_single_gpu"] = single == result
+            if n < (1 << 32):
+                back = rsn.lz.Decompress(result)
+                line["roundtrip_ok"] = back == bytes(enc.cpu().numpy())
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
