@@ -274,13 +274,24 @@ __device__ __forceinline__ void match_tile_body(const uint8_t *__restrict__ enc,
     {
         const uint32_t per = ((ev + WARPS - 1) / WARPS + 31) & ~31u;
         const uint32_t lo = min(ev, w * per), hi = min(ev, lo + per);
+        uint32_t nlong = 0;
         for (uint32_t c = lo; c < hi; c += 32) {
             const uint32_t r = c + lane;
-            bool head = false;
-            if (r < hi) head = r == 0 || ((lds32(s, arr[r]) ^ lds32(s, arr[r - 1])) & 0xFFFFFFu) != 0;
+            bool head = false, longnb = false;
+            if (r < hi) {
+                head = r == 0 || ((lds32(s, arr[r]) ^ lds32(s, arr[r - 1])) & 0xFFFFFFu) != 0;
+                // neighbours in (3-gram, position) order that agree on 7 bytes: a sample of how long
+                // the comparisons of this tile will run
+                longnb = !head && lds32(s, arr[r] + 3) == lds32(s, arr[r - 1] + 3);
+            }
             const unsigned hm = __ballot_sync(0xffffffffu, head);
-            if (lane == 0) sm.heads[c >> 5] = hm;
+            const unsigned lm = __ballot_sync(0xffffffffu, longnb);
+            if (lane == 0) {
+                sm.heads[c >> 5] = hm;
+                nlong += __popc(lm);
+            }
         }
+        if (lane == 0) sm.wtot[1 + w] = nlong;
     }
     for (int i = threadIdx.x; i < 16 * WARPS; i += THREADS) sm.ctr[i] = 0;
     if (threadIdx.x < 128) sm.diag[threadIdx.x] = 0;  // d = 0 never matches a real distance
@@ -352,6 +363,15 @@ __device__ __forceinline__ void match_tile_body(const uint8_t *__restrict__ enc,
         }
     }
     const uint32_t n_order = sm.wtot[0];
+    // Tiles in which most sorted neighbours agree beyond the 3-gram (log-like and repetitive data)
+    // take the voting form of the candidate loop below.
+    bool heavy;
+    {
+        uint32_t nl = 0;
+#pragma unroll
+        for (int k = 0; k < WARPS; k++) nl += sm.wtot[1 + k];
+        heavy = nl * 2 > ev;
+    }
 
     // ---- candidates, far to near; one thread per slot, slots of similar work side by side
     for (uint32_t k0 = w * 32; k0 < n_order; k0 += THREADS) {
@@ -372,10 +392,65 @@ __device__ __forceinline__ void match_tile_body(const uint8_t *__restrict__ enc,
         // Far to near.  A candidate at distance d yields at most min(d, room), so only slots with
         // arr[c] < jlim = e - best can win (the list is in position order), and a winner must match
         // the byte at offset `best` (tgt).  Lanes of a warp hold slots of one work class.
+        uint32_t jlim = 0, tgt = 0;
+        const uint8_t *sb = s;
         if (act && room > best) {
-            uint32_t jlim = e - best;
-            const uint8_t *sb = s + best;
-            uint32_t tgt = s[e + best];
+            jlim = e - best;
+            sb = s + best;
+            tgt = s[e + best];
+        } else {
+            c = r;
+        }
+        if (heavy) {
+            // Voting form: every lane first advances to its next candidate that survives the byte
+            // filter, then all lanes that have one compare together.  In the plain per-lane loop the
+            // comparison code ran with 3-4 of 32 lanes on log-like data (long comparisons behind a
+            // filter most candidates fail); on text the vote per step costs more than it saves.
+            for (;;) {
+                bool have = false;
+                uint32_t j = 0;
+                while (c < r) {
+                    j = arr[c];
+                    if (j >= jlim) {  // nearer candidates yield even less
+                        c = r;
+                        break;
+                    }
+                    c++;
+                    if (sb[j] == tgt) {
+                        have = true;
+                        break;
+                    }
+                }
+                if (!__any_sync(0xffffffffu, have)) break;
+                if (have) {
+                    const uint32_t d = e - j;
+                    const uint32_t cap = min(d, room);
+                    uint32_t l = 3;
+                    while (l < cap && l < 35) {
+                        const uint32_t x = lds32(s, j + l) ^ lds32(s, e + l);
+                        if (x) {
+                            l += (__ffs(x) - 1) >> 3;
+                            goto lcp_done_h;
+                        }
+                        l += 4;
+                    }
+                    if (l < cap) l = long_lcp(sm, s, e, d, l, cap, avail);
+                lcp_done_h:
+                    l = min(l, cap);
+                    if (l > best) {
+                        best = l;
+                        boff = e - j;
+                        if (room <= best) {
+                            c = r;
+                        } else {
+                            jlim = e - best;
+                            sb = s + best;
+                            tgt = s[e + best];
+                        }
+                    }
+                }
+            }
+        } else {
             for (; c < r; c++) {
                 const uint32_t j = arr[c];
                 if (j >= jlim) break;  // nearer candidates yield even less
