@@ -133,7 +133,7 @@ int lzss_escape(const uint8_t *d_in, size_t n, DevBuf &enc, const uint8_t **enc_
 constexpr int kPB = 4096;        // parse block (positions)
 constexpr int kPT = 256;         // threads per CTA
 constexpr int kPI = kPB / kPT;   // 16 consecutive positions per thread
-constexpr int kFan = 64;         // hierarchy fan-out
+constexpr int kFan = 16;         // hierarchy fan-out (single stream)
 
 struct ParseCfg {
     uint32_t W;            // effective window
@@ -292,12 +292,12 @@ __device__ __forceinline__ void parse_down_body(const uint16_t *__restrict__ E0,
                                                 int child_lvl, size_t rsize_child, size_t regions_parent,
                                                 size_t regions_child, uint32_t J, size_t n,
                                                 const uint64_t *__restrict__ entry_parent,
-                                                uint64_t *__restrict__ entry_child) {
+                                                uint64_t *__restrict__ entry_child, int fan) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= regions_parent) return;
     size_t p = entry_parent[r];
-    for (int c = 0; c < kFan; c++) {
-        const size_t cr = r * kFan + c;
+    for (int c = 0; c < fan; c++) {
+        const size_t cr = r * fan + c;
         if (cr >= regions_child) break;
         entry_child[cr] = p;
         const size_t end = (cr + 1) * rsize_child;
@@ -307,7 +307,8 @@ __device__ __forceinline__ void parse_down_body(const uint16_t *__restrict__ E0,
 __global__ void k_parse_down(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tchild, int child_lvl,
                              size_t rsize_child, size_t regions_parent, size_t regions_child, uint32_t J, size_t n,
                              const uint64_t *__restrict__ entry_parent, uint64_t *__restrict__ entry_child) {
-    parse_down_body(E0, Tchild, child_lvl, rsize_child, regions_parent, regions_child, J, n, entry_parent, entry_child);
+    parse_down_body(E0, Tchild, child_lvl, rsize_child, regions_parent, regions_child, J, n, entry_parent, entry_child,
+                    kFan);
 }
 
 // ============================================================================= K4 emit
@@ -711,6 +712,8 @@ int lzss_compress_dev_ex(const uint8_t *d_in, size_t n, int64_t window, int vari
 // escaping live in the LzFile records on the device; grids are sized for the largest possible file
 // and CTAs beyond a file's real size leave at once.
 
+constexpr int kBatchFan = 64;  // batches: at most two levels (files of <= 4 MiB)
+
 struct LzBatch {
     LzFile *files;
     uint32_t window;
@@ -731,7 +734,7 @@ struct LzBatch {
     uint64_t *bb, *bo;              // [G][bb_stride]
     size_t bb_stride;
     uint64_t *out_n;                // [G]
-    int top;                        // 0: one level of blocks; 1: blocks grouped kFan at a time
+    int top;                        // 0: one level of blocks; 1: blocks grouped kBatchFan at a time
 };
 
 __device__ __forceinline__ ParseCfg batch_cfg(const LzFile &f) {
@@ -778,7 +781,7 @@ __global__ void __launch_bounds__(kPT) kb_parse_exits(LzBatch b) {
 
 __global__ void kb_parse_up(LzBatch b) {  // grid: (rel chunks, level-1 regions, files)
     const LzFile &f = b.files[blockIdx.z];
-    const size_t rsize1 = (size_t)kPB * kFan;
+    const size_t rsize1 = (size_t)kPB * kBatchFan;
     if ((size_t)blockIdx.y * rsize1 >= f.en) return;
     parse_up_body(b.E0 + (size_t)blockIdx.z * b.e0_stride, nullptr, b.T1 + (size_t)blockIdx.z * b.t1_stride, 1, kPB,
                   rsize1, f.W, (size_t)f.en, blockIdx.y);
@@ -789,7 +792,7 @@ __global__ void kb_parse_top(LzBatch b, size_t G) {  // one thread per file
     if (y >= G) return;
     const LzFile &f = b.files[y];
     if (f.en == 0) return;
-    const size_t rsize = b.top ? (size_t)kPB * kFan : (size_t)kPB;
+    const size_t rsize = b.top ? (size_t)kPB * kBatchFan : (size_t)kPB;
     uint64_t *entry = b.top ? b.entry1 + y * b.entry1_stride : b.entry0 + y * b.entry0_stride;
     parse_top_body(b.E0 + y * b.e0_stride, b.top ? b.T1 + y * b.t1_stride : nullptr, b.top, rsize,
                    div_up_dev((size_t)f.en, rsize), f.W, (size_t)f.en, entry);
@@ -799,9 +802,9 @@ __global__ void kb_parse_down(LzBatch b) {  // top == 1: level-1 regions -> bloc
     const LzFile &f = b.files[blockIdx.y];
     if (f.en == 0) return;
     parse_down_body(b.E0 + (size_t)blockIdx.y * b.e0_stride, nullptr, 0, kPB,
-                    div_up_dev((size_t)f.en, (size_t)kPB * kFan), div_up_dev((size_t)f.en, (size_t)kPB), f.W,
+                    div_up_dev((size_t)f.en, (size_t)kPB * kBatchFan), div_up_dev((size_t)f.en, (size_t)kPB), f.W,
                     (size_t)f.en, b.entry1 + (size_t)blockIdx.y * b.entry1_stride,
-                    b.entry0 + (size_t)blockIdx.y * b.entry0_stride);
+                    b.entry0 + (size_t)blockIdx.y * b.entry0_stride, kBatchFan);
 }
 
 __global__ void __launch_bounds__(kPT) kb_emit_plan(LzBatch b) {
@@ -851,9 +854,9 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     const size_t tiles_cap = div_up(cap, kTile), blocks_cap = ecap / kPB;
     LzBatch b{};
     b.window = (uint32_t)window;
-    b.top = blocks_cap > (size_t)kFan ? 1 : 0;
-    const size_t regions1 = div_up(blocks_cap, kFan);
-    if (regions1 > (size_t)kFan) return RSN_ERR_UNSUPPORTED;
+    b.top = blocks_cap > (size_t)kBatchFan ? 1 : 0;
+    const size_t regions1 = div_up(blocks_cap, kBatchFan);
+    if (regions1 > (size_t)kBatchFan) return RSN_ERR_UNSUPPORTED;
     b.tc_stride = tiles_cap + 1;
     b.enc_stride = ecap + 256;
     b.packed_stride = ecap + 64;

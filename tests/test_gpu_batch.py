@@ -17,6 +17,9 @@ def _files():
     files += [synth.batch_file(100 + j, 48 * 1024) for j in range(12)]
     # escape-heavy and degenerate content
     files += [b"<\\" * 5000, b"\xff" * 9000, b"\\" * 4097, b"a" * 70000, b"ab" * 33000, bytes(range(256)) * 40]
+    # thousands of distinct multi-byte runes with tied frequencies: the heap replay decides the codes
+    files.append("".join(chr(0x100 + (i * 7919) % 5000) for i in range(6000)).encode())
+    files.append("".join(chr(0x800 + (i * 104729) % 40000) for i in range(30000)).encode())
     files += [b"", b"x"]
     files.append(synth.repetitive(300000, 7))   # > 64 parse blocks after escaping: two-level hierarchy
     files.append(synth.text(700000, 9))
