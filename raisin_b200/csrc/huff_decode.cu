@@ -484,15 +484,15 @@ void hdec_host_plan(const uint8_t *h, size_t n, HdecHost &pl) {
         return;
     }
     pl.max = nbits - pl.diff;
-    // the device builder packs (frequency sum, node) into one word: anything a header could say
-    // beyond that, and the single-leaf special cases, go through the single-stream call
+    // the device builder keeps (frequency sum, node) in one 64-bit word, 32 bits each: anything a
+    // header could say beyond that, and the single-leaf special cases, go through the single-stream call
     uint64_t sum = 0;
     bool fits = leaves.size() >= 2 && leaves.size() <= kTreeMaxLeaves;
     for (const HuffLeaf &l : leaves) {
         if (l.freq < 0 || l.freq >= ((int64_t)1 << 32)) fits = false;
         else sum += (uint64_t)l.freq;
     }
-    if (!fits || sum >= ((uint64_t)1 << 39)) {
+    if (!fits || sum >= ((uint64_t)1 << 32)) {
         pl.per_file = true;
         return;
     }

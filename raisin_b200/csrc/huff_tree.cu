@@ -17,7 +17,8 @@ namespace {
 
 constexpr int kLutBitsTree = 12;  // == kLutBits in huff_decode.cu
 
-__device__ __forceinline__ bool heap_less(uint64_t a, uint64_t b) { return (a >> 24) < (b >> 24); }
+// heap entry = (frequency sum << 32) | node: Less compares the high words only (huffman.go:43-45)
+__device__ __forceinline__ bool heap_less(uint64_t a, uint64_t b) { return (uint32_t)(a >> 32) < (uint32_t)(b >> 32); }
 
 // container/heap.down / up (Go 1.15) with the moving element carried in a register: the array ends
 // up exactly as after Go's swaps.
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(32) kb_huff_tree(TreeJob *__restrict__ jobs) {
     HuffNodeDev *nodes = job.nodes;
     uint32_t *parent = job.parent;
     for (int i = lane; i < k; i += 32) {
-        heap[i] = ((uint64_t)job.freq[i] << 24) | (uint64_t)i;
+        heap[i] = ((uint64_t)job.freq[i] << 32) | (uint64_t)i;
         nodes[i] = HuffNodeDev{-1, (int32_t)job.rune[i]};
     }
     __syncwarp();
@@ -73,16 +74,16 @@ __global__ void __launch_bounds__(32) kb_huff_tree(TreeJob *__restrict__ jobs) {
             const uint64_t b = heap[0];
             heap[0] = heap[--n];
             if (n > 0) heap_down(heap, 0, n);
-            const uint32_t an = (uint32_t)(a & 0xFFFFFFu), bn = (uint32_t)(b & 0xFFFFFFu);
+            const uint32_t an = (uint32_t)a, bn = (uint32_t)b;
             nodes[next] = HuffNodeDev{(int32_t)an, (int32_t)bn};  // left = first popped (huffman.go:96-99)
             parent[an] = (uint32_t)next;
             parent[bn] = (uint32_t)next | 0x80000000u;
-            heap[n] = (((a >> 24) + (b >> 24)) << 24) | (uint64_t)next;  // Push
+            heap[n] = (((a >> 32) + (b >> 32)) << 32) | (uint64_t)next;  // Push (sums stay below 2^32: checked by the host)
             heap_up(heap, n);
             n++;
             next++;
         }
-        root = (int)(heap[0] & 0xFFFFFFu);
+        root = (int)(uint32_t)heap[0];
         job.root = root;
     }
     root = __shfl_sync(0xffffffffu, root, 0);

@@ -10,11 +10,23 @@ if [ "${2:-}" != "summarize" ]; then
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:'k_match_tile$' -s 2 -c 1 -o gpurun_out/prof_k2_$R \
       python tools/prof_run.py match 64 text 3 > gpurun_out/prof.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/launches_batch_$R.csv \
+      python bench.py --workload batch --files 64 --steps 1 --warmup 3 --workers 1 > gpurun_out/ncu_batch.log 2>&1
   python bench.py 2>&1 | tail -1 > gpurun_out/bench_$R.json
+  python bench.py --workload batch 2>&1 | tail -1 > gpurun_out/bench_batch_$R.json
   exit 0
 fi
 cp gpurun_out/launches_$R.csv profiles/${R}_launches.csv
 cp gpurun_out/bench_$R.json profiles/${R}_bench_n1.json
+cp gpurun_out/bench_batch_$R.json profiles/${R}_bench_batch_n1.json
+cp gpurun_out/launches_batch_$R.csv profiles/${R}_launches_batch.csv
+{
+  echo "# $R: launch list of the batched small-file path (\`bench.py --workload batch --files 64 --workers 1\`: 64 x 256 KiB files = one 16 MiB group, lzss,huffman compress then decompress)"
+  echo
+  echo "Command: \`ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv python bench.py --workload batch --files 64 --steps 1 --warmup 3 --workers 1\` (first 260 launches; every kernel runs once per group, the file index is blockIdx.y)"
+  echo
+  python tools/summarize_launches.py gpurun_out/launches_batch_$R.csv
+} > profiles/${R}_launches_batch.md
 {
   echo "# $R: launch list of \`bench.py --steps 2 --warmup 3\` (64 MiB text stream: lzss compress+decompress, then the Huffman layer and the K2-only timing)"
   echo
