@@ -47,6 +47,8 @@ struct Smem {
     unsigned long long diag[16 * 8];  // 16 sets (d & 15) x 8 ways
 };
 
+constexpr int kVoteSteps = 8;  // candidates a lane may walk between two votes (3: 5.16 ms, 8: 4.99 ms, 16: 5.29 ms on 64 MiB text)
+
 __device__ __forceinline__ uint32_t lds32(const uint8_t *s, uint32_t pos) {
     const uint32_t a = pos & ~3u;
     const uint32_t lo = *reinterpret_cast<const uint32_t *>(s + a);
@@ -274,24 +276,13 @@ __device__ __forceinline__ void match_tile_body(const uint8_t *__restrict__ enc,
     {
         const uint32_t per = ((ev + WARPS - 1) / WARPS + 31) & ~31u;
         const uint32_t lo = min(ev, w * per), hi = min(ev, lo + per);
-        uint32_t nlong = 0;
         for (uint32_t c = lo; c < hi; c += 32) {
             const uint32_t r = c + lane;
-            bool head = false, longnb = false;
-            if (r < hi) {
-                head = r == 0 || ((lds32(s, arr[r]) ^ lds32(s, arr[r - 1])) & 0xFFFFFFu) != 0;
-                // neighbours in (3-gram, position) order that agree on 7 bytes: a sample of how long
-                // the comparisons of this tile will run
-                longnb = !head && lds32(s, arr[r] + 3) == lds32(s, arr[r - 1] + 3);
-            }
+            bool head = false;
+            if (r < hi) head = r == 0 || ((lds32(s, arr[r]) ^ lds32(s, arr[r - 1])) & 0xFFFFFFu) != 0;
             const unsigned hm = __ballot_sync(0xffffffffu, head);
-            const unsigned lm = __ballot_sync(0xffffffffu, longnb);
-            if (lane == 0) {
-                sm.heads[c >> 5] = hm;
-                nlong += __popc(lm);
-            }
+            if (lane == 0) sm.heads[c >> 5] = hm;
         }
-        if (lane == 0) sm.wtot[1 + w] = nlong;
     }
     for (int i = threadIdx.x; i < 16 * WARPS; i += THREADS) sm.ctr[i] = 0;
     if (threadIdx.x < 128) sm.diag[threadIdx.x] = 0;  // d = 0 never matches a real distance
@@ -363,15 +354,6 @@ __device__ __forceinline__ void match_tile_body(const uint8_t *__restrict__ enc,
         }
     }
     const uint32_t n_order = sm.wtot[0];
-    // Tiles in which most sorted neighbours agree beyond the 3-gram (log-like and repetitive data)
-    // take the voting form of the candidate loop below.
-    bool heavy;
-    {
-        uint32_t nl = 0;
-#pragma unroll
-        for (int k = 0; k < WARPS; k++) nl += sm.wtot[1 + k];
-        heavy = nl * 2 > ev;
-    }
 
     // ---- candidates, far to near; one thread per slot, slots of similar work side by side
     for (uint32_t k0 = w * 32; k0 < n_order; k0 += THREADS) {
@@ -401,83 +383,57 @@ __device__ __forceinline__ void match_tile_body(const uint8_t *__restrict__ enc,
         } else {
             c = r;
         }
-        if (heavy) {
-            // Voting form: every lane first advances to its next candidate that survives the byte
-            // filter, then all lanes that have one compare together.  In the plain per-lane loop the
-            // comparison code ran with 3-4 of 32 lanes on log-like data (long comparisons behind a
-            // filter most candidates fail); on text the vote per step costs more than it saves.
-            for (;;) {
-                bool have = false;
-                uint32_t j = 0;
-                while (c < r) {
-                    j = arr[c];
-                    if (j >= jlim) {  // nearer candidates yield even less
-                        c = r;
-                        break;
-                    }
-                    c++;
-                    if (sb[j] == tgt) {
-                        have = true;
-                        break;
-                    }
+        // The loop runs in warp-wide rounds: every lane walks up to kVoteSteps candidates of its list
+        // (most fail the byte filter) or until one survives, then all lanes that hold a survivor
+        // compare together.  With the comparison inside a plain per-lane walk it ran with 3-4 of 32
+        // lanes (text and logs alike); an unbounded walk per round left the walk itself at 7 lanes.
+        for (;;) {
+            bool have = false;
+            uint32_t j = 0;
+            // at most kVoteSteps candidates per lane and round: lanes that found a survivor wait
+            // only that long for the others, and a round still gathers survivors from many lanes
+#pragma unroll 1
+            for (int step = 0; step < kVoteSteps && c < r; step++) {
+                j = arr[c];
+                if (j >= jlim) {  // nearer candidates yield even less
+                    c = r;
+                    break;
                 }
-                if (!__any_sync(0xffffffffu, have)) break;
-                if (have) {
-                    const uint32_t d = e - j;
-                    const uint32_t cap = min(d, room);
-                    uint32_t l = 3;
-                    while (l < cap && l < 35) {
-                        const uint32_t x = lds32(s, j + l) ^ lds32(s, e + l);
-                        if (x) {
-                            l += (__ffs(x) - 1) >> 3;
-                            goto lcp_done_h;
-                        }
-                        l += 4;
-                    }
-                    if (l < cap) l = long_lcp(sm, s, e, d, l, cap, avail);
-                lcp_done_h:
-                    l = min(l, cap);
-                    if (l > best) {
-                        best = l;
-                        boff = e - j;
-                        if (room <= best) {
-                            c = r;
-                        } else {
-                            jlim = e - best;
-                            sb = s + best;
-                            tgt = s[e + best];
-                        }
-                    }
+                c++;
+                if (sb[j] == tgt) {
+                    have = true;
+                    break;
                 }
             }
-        } else {
-            for (; c < r; c++) {
-                const uint32_t j = arr[c];
-                if (j >= jlim) break;  // nearer candidates yield even less
-                if (sb[j] != tgt) continue;
+            if (!__any_sync(0xffffffffu, have)) {
+                if (!__any_sync(0xffffffffu, c < r)) break;
+                continue;
+            }
+            if (have) {
                 const uint32_t d = e - j;
                 const uint32_t cap = min(d, room);
                 uint32_t l = 3;
-                // short matches (the common case) stay in this tight loop; after 32 equal bytes the
-                // out-of-line routine takes over (diagonal cache)
                 while (l < cap && l < 35) {
                     const uint32_t x = lds32(s, j + l) ^ lds32(s, e + l);
                     if (x) {
                         l += (__ffs(x) - 1) >> 3;
-                        goto lcp_done;
+                        goto lcp_done_h;
                     }
                     l += 4;
                 }
                 if (l < cap) l = long_lcp(sm, s, e, d, l, cap, avail);
-            lcp_done:
+            lcp_done_h:
                 l = min(l, cap);
                 if (l > best) {
                     best = l;
                     boff = e - j;
-                    if (room <= best) break;
-                    jlim = e - best;
-                    sb = s + best;
-                    tgt = s[e + best];
+                    if (room <= best) {
+                        c = r;
+                    } else {
+                        jlim = e - best;
+                        sb = s + best;
+                        tgt = s[e + best];
+                    }
                 }
             }
         }
