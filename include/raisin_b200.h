@@ -89,12 +89,16 @@ int rsn_compress_layers(const char *algorithms, const uint8_t *in, size_t n, uin
 int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
 
 /*
- * Batches of independent files (BASELINE configs[3]): file i is compressed (or decompressed) with
- * the layer list exactly as rsn_compress_layers would, on a pool of `workers` host threads (0 =
- * default), each with its own CUDA stream, so many small per-file pipelines overlap on the GPU.
- * out[i]/out_n[i] receive library-owned buffers (rsn_free each); rcs[i] (optional) the per-file
- * code.  Returns RSN_OK or the first failing file's code.  With device != 0 the in/out pointers
- * are device pointers (release with rsn_dev_free(p, NULL)).
+ * Batches of independent files (BASELINE configs[3]; what engine.BenchmarkSuite's per-file loop does,
+ * engine.go:208-262): file i is compressed (or decompressed) with the layer list exactly as
+ * rsn_compress_layers would.  Host buffers (device == 0): files of up to 4 MiB are cut into groups
+ * of about 16 MiB and every kernel of a stage runs once per group (the file index is a grid
+ * dimension), so a small file costs no kernel launches or synchronisations of its own; groups, and
+ * the files that go one by one (empty, larger than 4 MiB), are spread over `workers` host threads
+ * (0 = default), each with its own CUDA stream.  out[i]/out_n[i] receive library-owned buffers
+ * (rsn_free each); rcs[i] (optional) the per-file code: a file the reference would panic on fails
+ * alone.  Returns RSN_OK or the first failing file's code.  With device != 0 the in/out pointers
+ * are device pointers (release with rsn_dev_free(p, NULL)) and files go one by one.
  */
 int rsn_batch_layers(const char *algorithms, int compress, size_t count, const uint8_t *const *in, const size_t *in_n,
                      uint8_t **out, size_t *out_n, int *rcs, int workers, int device);

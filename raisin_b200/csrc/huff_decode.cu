@@ -217,7 +217,6 @@ __global__ void k_hdec_write(DecParams p, size_t subs, const uint64_t *__restric
 int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int strict, uint8_t **d_out, size_t *out_n,
                         cudaStream_t s) {
     ArenaScope scope(s);
-    Ctx &c = ctx();
     Trace tr("hd", s);
     // ---- host: find the first 5C 0A (strings.SplitN, huffman.go:261) and parse the header
     std::vector<uint8_t> h_copy;
@@ -365,7 +364,6 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
     RSN_TRY(read_u64(flag.as<uint64_t>(), &err, s));
     tr.mark("write");
     if ((uint32_t)err) return RSN_ERR_TRUNCATED;
-    (void)c;
     *d_out = (uint8_t *)out.release();
     *out_n = (size_t)total;
     return RSN_OK;
@@ -600,7 +598,6 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
     if (subs_total) RSN_TRY(huff_tree_batch(djobs.as<TreeJob>(), G, kmax, s));
     RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HdecFile), cudaMemcpyHostToDevice, s));
     const dim3 grid((unsigned)div_up(subs_cap, 128), (unsigned)G);
-    Ctx &c = ctx();
     tr.mark("tables");
     if (subs_total) {
         RSN_LAUNCH(kb_hdec_init, grid, 128, 0, s, files.as<HdecFile>(), start.as<uint64_t>(), endA.as<uint64_t>(),
@@ -656,7 +653,6 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         out.n[f] = rn;
         out.owned.push_back(r);
     }
-    (void)c;
     return RSN_OK;
 }
 

@@ -320,7 +320,6 @@ __global__ void __launch_bounds__(kTileThreads) k_enc_write(const uint8_t *__res
 int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s) {
     ArenaScope scope(s);
     if (n == 0) return RSN_ERR_EMPTY_INPUT;
-    Ctx &c = ctx();
     const size_t tiles = div_up(n, kTile);
 
     Trace tr("hc", s);
@@ -401,7 +400,6 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     tr.mark("encode");
     // h_codes / pre are read by async copies: wait before they go out of scope
     RSN_CUDA(cudaStreamSynchronize(s));
-    (void)c;
     *d_out = (uint8_t *)out.release();
     *out_n = total;
     return RSN_OK;

@@ -845,7 +845,6 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     if (G == 0) return RSN_OK;
     if (window < 1 || window > 4096) return RSN_ERR_UNSUPPORTED;
     ArenaScope scope(s);
-    Ctx &c = ctx();
     size_t cap = 1;
     for (size_t f = 0; f < G; f++)
         if (in.rc[f] == RSN_OK) cap = std::max<size_t>(cap, in.n[f]);
@@ -937,7 +936,6 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     RSN_LAUNCH(kb_emit_write, dim3((unsigned)blocks_cap, g), kPT, 0, s, b, outp.as<uint8_t *>());
     RSN_CUDA(cudaStreamSynchronize(s));  // h_outp is read by the copy above
     out.owned.push_back(res.release());
-    (void)c;
     return RSN_OK;
 }
 
