@@ -43,13 +43,13 @@ __device__ __forceinline__ T block_inclusive_scan_generic(T v, T *buf, Op op) {
 enum : uint8_t { ST_OPEN = 0, ST_SEP = 1, ST_CLOSE = 2 };
 constexpr uint8_t kMapId = 0x24;  // f(0)=0, f(1)=1, f(2)=2, two bits each
 
-__device__ __forceinline__ uint8_t tok_map_of(uint8_t b) {
+__host__ __device__ constexpr uint8_t tok_map_of(uint8_t b) {
     // lzss.go:333-360: '<' acts only in Open, ',' only in Sep, '>' only in Close
     return b == 0x3C ? 0x25 : b == 0x2C ? 0x28 : b == 0x3E ? 0x04 : kMapId;
 }
-__device__ __forceinline__ uint8_t map_apply(uint8_t m, uint8_t st) { return (m >> (2 * st)) & 3; }
+__host__ __device__ constexpr uint8_t map_apply(uint8_t m, uint8_t st) { return (m >> (2 * st)) & 3; }
 // first a, then b
-__device__ __forceinline__ uint8_t map_compose(uint8_t a, uint8_t b) {
+__host__ __device__ constexpr uint8_t map_compose(uint8_t a, uint8_t b) {
     return (uint8_t)(map_apply(b, map_apply(a, 0)) | (map_apply(b, map_apply(a, 1)) << 2) |
                      (map_apply(b, map_apply(a, 2)) << 4));
 }
@@ -57,26 +57,71 @@ struct MapCompose {
     __device__ uint8_t operator()(uint8_t a, uint8_t b) const { return map_compose(a, b); }
 };
 
-__device__ __forceinline__ uint8_t thread_map(const uint8_t (&v)[16], int valid) {
-    uint8_t m = kMapId;
+// Composition costs ~20 integer operations and runs once per input byte: the kernels look it up
+// instead.  lut[a * 64 + b] = map_compose(a, b) for all 6-bit maps, built at compile time, copied
+// to shared memory by each CTA.
+struct alignas(16) MapLut {
+    uint8_t v[64 * 64];
+};
+constexpr MapLut make_map_lut() {
+    MapLut l{};
+    for (int a = 0; a < 64; a++)
+        for (int b = 0; b < 64; b++) l.v[a * 64 + b] = map_compose((uint8_t)a, (uint8_t)b);
+    return l;
+}
+__device__ const MapLut g_map_lut = make_map_lut();
+
+__device__ __forceinline__ void load_map_lut(uint8_t *lut) {  // 4096 bytes, blockDim.x >= 256
+    const uint4 *src = reinterpret_cast<const uint4 *>(g_map_lut.v);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint4 *>(lut)[i] = src[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint8_t thread_map(const uint8_t (&v)[16], int valid, const uint8_t *lut) {
+    uint32_t m = kMapId;
 #pragma unroll
     for (int k = 0; k < 16; k++)
-        if (k < valid) m = map_compose(m, tok_map_of(v[k]));
-    return m;
+        if (k < valid) m = lut[m * 64 + tok_map_of(v[k])];
+    return (uint8_t)m;
+}
+
+// Exclusive scan of the threads' maps in thread order (blockDim.x a multiple of 32, <= 1024):
+// returns the composition of all earlier threads' maps; *total (if not null) receives the
+// composition of the whole CTA.  wt: one byte per warp + 1.
+__device__ __forceinline__ uint8_t block_exclusive_map(uint8_t m, const uint8_t *lut, uint8_t *wt, uint8_t *total) {
+    const unsigned lane = lane_id(), wid = warp_id(), nw = (blockDim.x + 31) >> 5;
+    uint32_t v = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v = lut[o * 64 + v];
+    }
+    if (lane == 31) wt[wid] = (uint8_t)v;
+    __syncthreads();
+    uint32_t pre = kMapId;
+    for (unsigned k = 0; k < wid; k++) pre = lut[pre * 64 + wt[k]];
+    uint32_t exc = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) exc = kMapId;
+    exc = lut[pre * 64 + exc];
+    if (total && threadIdx.x == blockDim.x - 1) *total = lut[pre * 64 + v];
+    (void)nw;
+    return (uint8_t)exc;
 }
 
 __device__ __forceinline__ void tok_reduce_body(const uint8_t *__restrict__ in, size_t n,
                                                 uint8_t *__restrict__ tile_map) {
-    __shared__ uint8_t buf[kTileThreads];
+    __shared__ __align__(16) uint8_t lut[64 * 64];
+    __shared__ uint8_t wt[33];
+    load_map_lut(lut);
     const size_t base = (size_t)blockIdx.x * kTile + (size_t)threadIdx.x * kItems;
     uint8_t m = kMapId;
     if (base < n) {
         uint8_t v[16];
         load16(in, base, n, 0, v);
-        m = thread_map(v, (int)min((size_t)16, n - base));
+        m = thread_map(v, (int)min((size_t)16, n - base), lut);
     }
-    m = block_inclusive_scan_generic<uint8_t>(m, buf, MapCompose());
-    if (threadIdx.x == blockDim.x - 1) tile_map[blockIdx.x] = m;
+    const uint8_t exc = block_exclusive_map(m, lut, wt, nullptr);
+    if (threadIdx.x == blockDim.x - 1) tile_map[blockIdx.x] = lut[exc * 64 + m];
 }
 __global__ void __launch_bounds__(kTileThreads) k_tok_reduce(const uint8_t *__restrict__ in, size_t n,
                                                              uint8_t *__restrict__ tile_map) {
@@ -86,19 +131,30 @@ __global__ void __launch_bounds__(kTileThreads) k_tok_reduce(const uint8_t *__re
 // state in front of each tile, starting from Open
 __device__ __forceinline__ void tok_spine_body(const uint8_t *__restrict__ tile_map, size_t tiles,
                                                uint8_t *__restrict__ tile_state) {
-    __shared__ uint8_t buf[1024];
+    __shared__ __align__(16) uint8_t lut[64 * 64];
+    __shared__ uint8_t wt[34];
+    load_map_lut(lut);
     uint8_t carry = ST_OPEN;
-    for (size_t base = 0; base < tiles; base += blockDim.x) {
-        const size_t t = base + threadIdx.x;
-        uint8_t m = t < tiles ? tile_map[t] : kMapId;
-        uint8_t inc = block_inclusive_scan_generic<uint8_t>(m, buf, MapCompose());
-        // exclusive prefix = inclusive of the previous thread
-        uint8_t exc = threadIdx.x ? buf[threadIdx.x - 1] : kMapId;
-        if (t < tiles) tile_state[t] = map_apply(exc, carry);
-        const uint8_t last = buf[blockDim.x - 1];
+    // 16 consecutive tiles per thread: one scan round covers 16 * blockDim.x tiles
+    for (size_t base = 0; base < tiles; base += (size_t)blockDim.x * 16) {
+        const size_t t0 = base + (size_t)threadIdx.x * 16;
+        uint8_t mt[16];
+        uint32_t m = kMapId;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            mt[k] = t0 + k < tiles ? tile_map[t0 + k] : kMapId;
+            m = lut[m * 64 + mt[k]];
+        }
+        uint8_t *total = &wt[33];
+        uint32_t pre = block_exclusive_map((uint8_t)m, lut, wt, total);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (t0 + k < tiles) tile_state[t0 + k] = map_apply((uint8_t)pre, carry);
+            pre = lut[pre * 64 + mt[k]];
+        }
         __syncthreads();
-        carry = map_apply(last, carry);
-        (void)inc;
+        carry = map_apply(*total, carry);
+        __syncthreads();
     }
 }
 __global__ void __launch_bounds__(1024) k_tok_spine(const uint8_t *__restrict__ tile_map, size_t tiles,
@@ -189,9 +245,12 @@ __device__ __forceinline__ void tok_tile_body(const uint8_t *__restrict__ in, si
                                               const uint64_t *__restrict__ tile_off, uint64_t *__restrict__ tile_out,
                                               uint8_t *__restrict__ sb, uint32_t *__restrict__ dist,
                                               uint32_t *__restrict__ err) {
-    __shared__ uint8_t buf[kTileThreads];
+    __shared__ __align__(16) uint8_t lut[64 * 64];
+    __shared__ uint8_t wt[33];
     __shared__ uint64_t sm64[33];
     __shared__ uint32_t sm32[33];
+    __shared__ uint32_t n_long;
+    __shared__ uint16_t long_list[WRITE ? kMaxTok : 1];
     __shared__ uint16_t list[kMaxTok];
     __shared__ uint64_t tcnt[kMaxTok];
     __shared__ uint64_t tptr[WRITE ? kMaxTok : 1];
@@ -201,13 +260,14 @@ __device__ __forceinline__ void tok_tile_body(const uint8_t *__restrict__ in, si
     uint8_t v[16];
     int valid = 0;
     uint8_t m = kMapId;
+    if (WRITE && threadIdx.x == 0) n_long = 0;
+    load_map_lut(lut);
     if (base < n) {
         load16(in, base, n, 0, v);
         valid = (int)min((size_t)16, n - base);
-        m = thread_map(v, valid);
+        m = thread_map(v, valid, lut);
     }
-    block_inclusive_scan_generic<uint8_t>(m, buf, MapCompose());
-    const uint8_t exc = threadIdx.x ? buf[threadIdx.x - 1] : kMapId;
+    const uint8_t exc = block_exclusive_map(m, lut, wt, nullptr);
     uint8_t st = map_apply(exc, tile_state[blockIdx.x]);
     uint32_t lit_mask = 0, open_mask = 0, flags = 0;
 #pragma unroll
@@ -279,17 +339,17 @@ __device__ __forceinline__ void tok_tile_body(const uint8_t *__restrict__ in, si
             continue;
         }
         if (cnt == 0) continue;
-        if (cnt <= 256) {
-            for (uint64_t q = 0; q < cnt; q++) dist[off + q] = (uint32_t)ptr;
-            tcnt[t] = 0;  // done; longer ones are filled by the whole CTA below
+        if (cnt > 256) {  // long runs are filled by the whole CTA below
+            long_list[atomicAdd(&n_long, 1u)] = (uint16_t)t;
+            continue;
         }
+        for (uint64_t q = 0; q < cnt; q++) dist[off + q] = (uint32_t)ptr;
     }
     __syncthreads();
-    for (uint32_t t = 0; t < T; t++) {
-        const uint64_t cnt = tcnt[t];
-        if (cnt <= 256) continue;
-        const uint64_t ptr = tptr[t], off = toff[t];
-        if (ptr > off) continue;
+    const uint32_t nl = n_long;
+    for (uint32_t i = 0; i < nl; i++) {
+        const uint32_t t = long_list[i];
+        const uint64_t cnt = tcnt[t], ptr = tptr[t], off = toff[t];
         for (uint64_t q = threadIdx.x; q < cnt; q += blockDim.x) dist[off + q] = (uint32_t)ptr;
     }
 }
