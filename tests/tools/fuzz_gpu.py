@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """Randomised parity run: GPU path vs oracle on structured random inputs (all ops, both LZSS
-variants, several windows).  usage: python tools/fuzz_gpu.py [seconds=120] [seed=0]"""
+variants, several windows).  usage: python tests/tools/fuzz_gpu.py [seconds=120] [seed=0]"""
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 

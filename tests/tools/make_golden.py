@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Regenerate tests/golden/vectors.json from the CPU oracle (oracle/raisin_oracle.c).
 
-Run from the repo root:  python tools/make_golden.py
+Run from the repo root:  python tests/tools/make_golden.py
 The fixtures pin the oracle's outputs on the named cases of tests/cases.py so that (a) the
 oracle cannot drift silently and (b) the GPU parity tests have expectations that do not
 depend on the oracle library being rebuilt identically.  Small outputs are stored as hex,
@@ -12,7 +12,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """BASELINE configs[2]: layered lzss,huffman on a large synthetic mixed corpus (text + repetitive
 logs + random bytes) on one B200, checked byte for byte against the CPU oracle, with timings.
-usage: python tools/validate_large.py [MiB=1024]"""
+usage: python tests/tools/validate_large.py [MiB=1024]"""
 import hashlib
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import raisin_b200 as rsn  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402

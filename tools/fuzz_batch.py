@@ -2,7 +2,7 @@
 """Randomised check of the batched small-file path: rsn_batch_layers over random groups of files
 (valid inputs, escape-heavy junk, corrupted and arbitrary "compressed" streams) must give, file by
 file, exactly what the single-stream C-ABI calls give (those are checked against the oracle by
-tools/fuzz_gpu.py and the parity tests).  usage: python tools/fuzz_batch.py [seconds=90] [seed=0]"""
+tests/tools/fuzz_gpu.py and the parity tests).  usage: python tools/fuzz_batch.py [seconds=90] [seed=0]"""
 import os
 import sys
 import time
