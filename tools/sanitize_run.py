@@ -29,5 +29,10 @@ for d in datas:
         rsn.engine.decompress_fused(x, ["lzss", "huffman"])
     except rsn.RaisinPanic:
         pass
-print(rsn.engine.batch(datas, ["lzss", "huffman"], True, workers=3) is not None)
+# the batched small-file path (kb_* kernels, device tree builder), both directions, incl. junk streams
+files = datas + [synth.batch_file(j, 30000) for j in range(6)] + [b"", "".join(chr(0x100 + i) for i in range(900)).encode()]
+for algos in (["lzss"], ["huffman"], ["lzss", "huffman"]):
+    got = rsn.engine.batch(files, algos, True, workers=2)
+    streams = [g if g is not None else b"junk<9,4>" for g in got] + [b"abc<9,4>def", b"no separator", b"3|a1|b\\\n\x00\xff"]
+    rsn.engine.batch(streams, algos, False, workers=2)
 print("sanitize run ok")
