@@ -5,7 +5,7 @@
 // Each input byte is a transition function on those three states, so the state in front of
 // every byte is an exclusive scan under function composition — exact for ANY input, not only
 // for streams our compressor produced.
-//   K5a  token-state scan (tile maps -> spine -> per-byte state)
+//   K5a  token-state scan (tile maps -> spine -> per-byte state); maps composed by table look-up
 //   K5b  per-token (ptr,cnt) parse with strconv.Atoi semantics, output sizes, offsets
 //   K5c  scatter literals and per-byte source distances
 //   K6   back-reference resolve by bounded pointer chasing with path compression
@@ -53,10 +53,6 @@ __host__ __device__ constexpr uint8_t map_compose(uint8_t a, uint8_t b) {
     return (uint8_t)(map_apply(b, map_apply(a, 0)) | (map_apply(b, map_apply(a, 1)) << 2) |
                      (map_apply(b, map_apply(a, 2)) << 4));
 }
-struct MapCompose {
-    __device__ uint8_t operator()(uint8_t a, uint8_t b) const { return map_compose(a, b); }
-};
-
 // Composition costs ~20 integer operations and runs once per input byte: the kernels look it up
 // instead.  lut[a * 64 + b] = map_compose(a, b) for all 6-bit maps, built at compile time, copied
 // to shared memory by each CTA.
@@ -369,9 +365,8 @@ constexpr int kHops = 64;
 // Every referenced byte follows its source chain to a literal.  Chains longer than kHops are
 // shortened in place (dist[o] := distance to the furthest ancestor reached) and finished by a
 // later round; both the old and the new distance name a true ancestor, so concurrent readers
-// are safe.  Literal bytes (dist == 0) are never written here.
-// `work` == nullptr: first round, one thread per output byte; unfinished bytes are appended to
-// `work_out`.  Later rounds walk the previous round's list only.
+// are safe.  Literal bytes (dist == 0) are never written here.  Bytes that could not be finished are
+// appended to `work_out`; later rounds walk that list only.
 __device__ __forceinline__ void resolve_one(uint8_t *__restrict__ sb, uint32_t *__restrict__ dist, size_t o,
                                             uint32_t d, uint32_t *__restrict__ work_out,
                                             uint32_t *__restrict__ work_count) {
