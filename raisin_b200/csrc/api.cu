@@ -414,21 +414,31 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
         const long v = atol(e);
         if (v >= 1 && v <= 1024) kGroupBytes = (size_t)v << 20;
     }
+    // The kernels of a group size their per-file arrays for the group's LARGEST file, so a group only
+    // holds files of one size class (within a factor of two; everything below 4 KiB is one class):
+    // memory stays proportional to the bytes in the group whatever the mix of sizes.
     std::vector<std::vector<size_t>> groups;
     std::vector<size_t> singles;
     if (!device) {
-        size_t bytes = 0;
+        struct Open {
+            long group = -1;
+            size_t bytes = 0;
+        };
+        Open open[64];
         for (size_t i = 0; i < count; i++) {
             if (in_n[i] == 0 || in_n[i] > kBatchMaxFile || !in[i]) {
                 singles.push_back(i);
                 continue;
             }
-            if (groups.empty() || bytes + in_n[i] > kGroupBytes || groups.back().size() >= kGroupFiles) {
+            const int cls = in_n[i] < 4096 ? 11 : 63 - __builtin_clzll((unsigned long long)in_n[i]);
+            Open &o = open[cls];
+            if (o.group < 0 || o.bytes + in_n[i] > kGroupBytes || groups[(size_t)o.group].size() >= kGroupFiles) {
                 groups.emplace_back();
-                bytes = 0;
+                o.group = (long)groups.size() - 1;
+                o.bytes = 0;
             }
-            groups.back().push_back(i);
-            bytes += in_n[i];
+            groups[(size_t)o.group].push_back(i);
+            o.bytes += in_n[i];
         }
     } else {
         for (size_t i = 0; i < count; i++) singles.push_back(i);

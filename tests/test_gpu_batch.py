@@ -65,6 +65,22 @@ def test_batch_layered_matches_per_file_calls(rsn):
         assert b == rsn.engine.decompress(g, algos)
 
 
+def test_batch_mixed_sizes_group_by_size_class(rsn):
+    """Hundreds of tiny files next to a few large ones: groups hold one size class each, so the
+    per-file arrays (sized for a group's largest file) stay proportional to the data."""
+    files = [synth.batch_file(j, 100 + 37 * (j % 50)) for j in range(600)]
+    files[17] = synth.text(3 << 20, 5)
+    files[400] = synth.logs(2 << 20, 6)
+    files[599] = synth.random_bytes(4 << 20, 7)
+    algos = ["lzss", "huffman"]
+    got = rsn.engine.batch(files, algos, True, workers=3)
+    for j in (0, 16, 17, 18, 399, 400, 599):
+        assert got[j] == rsn.engine.compress(files[j], algos), j
+    back = rsn.engine.batch(got, algos, False, workers=3)
+    for j in (0, 17, 400, 555, 599):
+        assert back[j] == rsn.engine.decompress(got[j], algos), j
+
+
 def test_batch_bad_streams_fail_alone(rsn):
     """A file the reference would panic on must not take its group down."""
     ok = synth.text(30000, 4)
