@@ -809,7 +809,9 @@ int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
         total += (h[f].sbn + 16 + 255) & ~(uint64_t)255;
         sb_cap = std::max<size_t>(sb_cap, h[f].sbn);
     }
-    if (total > ((size_t)1 << 30)) return RSN_ERR_UNSUPPORTED;  // the per-file path takes such groups
+    // distances and work lists take 12 bytes per decoded byte: groups that decode to more than
+    // 256 MiB go file by file
+    if (total > ((size_t)256 << 20)) return RSN_ERR_UNSUPPORTED;
     // ---- phase B: literals and distances, then the chase
     DevBuf sb, dist, wl[2], cnt;
     RSN_TRY(sb.alloc_out(total + 256, s));

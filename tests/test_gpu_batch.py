@@ -81,6 +81,25 @@ def test_batch_mixed_sizes_group_by_size_class(rsn):
         assert back[j] == rsn.engine.decompress(got[j], algos), j
 
 
+def test_batch_stage_fallbacks(rsn):
+    """Stages the batched kernels decline run file by file inside the same call: Huffman decode that
+    is not the first layer (no host copy of the header), and groups that decode to more than the
+    group limit (long runs)."""
+    files = [synth.batch_file(j, 20000 + 1000 * j) for j in range(9)]
+    algos = ["huffman", "lzss"]
+    got = rsn.engine.batch(files, algos, True, workers=2)
+    for f, g in zip(files, got):
+        assert g == rsn.engine.compress(f, algos)
+    back = rsn.engine.batch(got, algos, False, workers=2)
+    for g, b in zip(got, back):
+        assert b == rsn.engine.decompress(g, algos)
+    runs = [bytes([0x61 + j]) * (40 << 20) for j in range(8)]       # 320 MiB out of ~8 x 110 KB in
+    lz = [rsn.lz.CompressAsync(r, False, 4096) for r in runs[:1]]
+    small = [lz[0].replace(b"a", bytes([0x61 + j])) for j in range(8)]
+    back = rsn.engine.batch(small, ["lzss"], False, workers=1)
+    assert [len(b) for b in back] == [40 << 20] * 8 and back[3] == runs[3]
+
+
 def test_batch_bad_streams_fail_alone(rsn):
     """A file the reference would panic on must not take its group down."""
     ok = synth.text(30000, 4)
