@@ -141,7 +141,7 @@ int rsn_dev_lzss_escape(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
 
 /* ---- introspection ----------------------------------------------------------------------- */
 
-/* Number of kernels this library has launched from the calling thread since the last reset. */
+/* Number of kernels this library has launched (from any thread) since the last reset. */
 uint64_t rsn_kernel_launches(void);
 void rsn_reset_kernel_launches(void);
 /* "raisin_b200 <version> sm_100a" */

@@ -25,6 +25,7 @@ struct Ctx {
 
 Ctx &ctx();
 int ensure_ctx();
+void count_launch();  // this thread's counter and the process-wide one behind rsn_kernel_launches()
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 #define RSN_CUDA(expr)                                                       \
@@ -43,7 +44,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 #define RSN_LAUNCH(kernel, grid, block, smem, stream, ...)                   \
     do {                                                                     \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
-        ::rsn::ctx().launches++;                                             \
+        ::rsn::count_launch();                                               \
         RSN_CUDA(cudaGetLastError());                                        \
     } while (0)
 

@@ -1,6 +1,7 @@
 // context.cu — per-thread context, error plumbing, buffer pools, spine scan, library lifetime.
 #include "common.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,6 +15,12 @@ namespace rsn {
 static thread_local Ctx g_ctx;
 
 Ctx &ctx() { return g_ctx; }
+
+static std::atomic<uint64_t> g_launches{0};  // all threads (batch workers launch from their own)
+void count_launch() {
+    g_ctx.launches++;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
 
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     Ctx &c = ctx();
@@ -510,8 +517,8 @@ void rsn_dev_free(void *d_ptr, void *stream) {
     rsn::out_free(d_ptr, s);
 }
 
-uint64_t rsn_kernel_launches(void) { return rsn::ctx().launches; }
-void rsn_reset_kernel_launches(void) { rsn::ctx().launches = 0; }
+uint64_t rsn_kernel_launches(void) { return rsn::g_launches.load(); }
+void rsn_reset_kernel_launches(void) { rsn::g_launches.store(0); }
 const char *rsn_version(void) { return "raisin_b200 0.1 sm_100a"; }
 
 }  // extern "C"
