@@ -264,7 +264,6 @@ def main():
         run_batch(args, rank, local_rank, world)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 

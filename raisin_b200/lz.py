@@ -9,8 +9,6 @@ Errors are raised as RaisinPanic (the reference panics).
 """
 from __future__ import annotations
 
-import io
-
 from . import _lib
 from ._lib import RSN_LZSS_ASYNC, RSN_LZSS_ITER
 
