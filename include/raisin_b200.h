@@ -102,6 +102,13 @@ int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, u
  */
 int rsn_batch_layers(const char *algorithms, int compress, size_t count, const uint8_t *const *in, const size_t *in_n,
                      uint8_t **out, size_t *out_n, int *rcs, int workers, int device);
+/*
+ * The grouping rsn_batch_layers applies to host-buffer files of these sizes (host logic only; needs
+ * no device): group_of[i] = index of the group file i travels in, or -1 for the per-file path
+ * (empty files, files above 4 MiB).  A group holds files of one size class (within a factor of
+ * two of each other; everything below 4 KiB is one class), at most 512 files and about 16 MiB.
+ */
+int rsn_batch_plan(size_t count, const size_t *in_n, int64_t *group_of, size_t *n_groups);
 
 /* ---- device-buffer API ------------------------------------------------------------------- */
 /*

@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, "libraisin_b200.so")
 EXPORTS = [
     "rsn_init", "rsn_shutdown", "rsn_strerror", "rsn_last_cuda_error", "rsn_free", "rsn_host_alloc",
     "rsn_host_free", "rsn_lzss_compress", "rsn_lzss_decompress", "rsn_huff_compress", "rsn_huff_decompress",
-    "rsn_compress_layers", "rsn_decompress_layers", "rsn_batch_layers", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
+    "rsn_compress_layers", "rsn_decompress_layers", "rsn_batch_layers", "rsn_batch_plan", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
     "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_free", "rsn_dev_download", "rsn_dev_upload",
     "rsn_dev_lzss_match", "rsn_dev_lzss_emit", "rsn_dev_lzss_escape",
     "rsn_kernel_launches", "rsn_reset_kernel_launches", "rsn_version",
@@ -71,6 +71,8 @@ def lib():
     L.rsn_batch_layers.argtypes = [C.c_char_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int]
     L.rsn_batch_layers.restype = C.c_int
+    L.rsn_batch_plan.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, szp]
+    L.rsn_batch_plan.restype = C.c_int
     vpp = C.POINTER(C.c_void_p)
     L.rsn_dev_lzss_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_int64, C.c_int, vpp, szp, C.c_void_p]
     L.rsn_dev_lzss_decompress.argtypes = [C.c_void_p, C.c_size_t, vpp, szp, C.c_void_p]

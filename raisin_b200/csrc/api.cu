@@ -278,6 +278,47 @@ extern "C" {
 }  // extern "C"
 
 namespace rsn {
+// Which files of a batch travel together.  groups[g] lists the files of group g (every kernel of a
+// stage runs once per group), `singles` the files that go through the per-file path: empty files,
+// files above kBatchMaxFile, null inputs, and everything in a device-resident batch.
+// The kernels of a group size their per-file arrays for the group's LARGEST file, so a group only
+// holds files of one size class (within a factor of two; everything below 4 KiB is one class):
+// memory stays proportional to the bytes in the group whatever the mix of sizes.  `in` may be null
+// (planning only).
+void batch_plan(size_t count, const uint8_t *const *in, const size_t *in_n, int device,
+                std::vector<std::vector<size_t>> &groups, std::vector<size_t> &singles) {
+    size_t group_bytes = (size_t)16 << 20;
+    constexpr size_t kGroupFiles = 512;
+    if (const char *e = getenv("RSN_BATCH_GROUP_MIB")) {  // tuning knob
+        const long v = atol(e);
+        if (v >= 1 && v <= 1024) group_bytes = (size_t)v << 20;
+    }
+    if (device) {
+        for (size_t i = 0; i < count; i++) singles.push_back(i);
+        return;
+    }
+    struct Open {
+        long group = -1;
+        size_t bytes = 0;
+    };
+    Open open[64];
+    for (size_t i = 0; i < count; i++) {
+        if (in_n[i] == 0 || in_n[i] > kBatchMaxFile || (in && !in[i])) {
+            singles.push_back(i);
+            continue;
+        }
+        const int cls = in_n[i] < 4096 ? 11 : 63 - __builtin_clzll((unsigned long long)in_n[i]);
+        Open &o = open[cls];
+        if (o.group < 0 || o.bytes + in_n[i] > group_bytes || groups[(size_t)o.group].size() >= kGroupFiles) {
+            groups.emplace_back();
+            o.group = (long)groups.size() - 1;
+            o.bytes = 0;
+        }
+        groups[(size_t)o.group].push_back(i);
+        o.bytes += in_n[i];
+    }
+}
+
 static std::atomic<int> g_batch_host_threads{4};
 int batch_host_threads() { return g_batch_host_threads.load(); }
 void set_batch_host_threads(int t) { g_batch_host_threads.store(t < 1 ? 1 : t); }
@@ -390,6 +431,20 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
 
 extern "C" {
 
+// The grouping rsn_batch_layers would apply to files of these sizes (host logic only, no device
+// needed): group_of[i] = group index of file i, or -1 if it goes through the per-file path.
+int rsn_batch_plan(size_t count, const size_t *in_n, int64_t *group_of, size_t *n_groups) {
+    if ((!in_n || !group_of) && count) return RSN_ERR_INVALID_ARG;
+    std::vector<std::vector<size_t>> groups;
+    std::vector<size_t> singles;
+    batch_plan(count, nullptr, in_n, 0, groups, singles);
+    for (size_t i : singles) group_of[i] = -1;
+    for (size_t g = 0; g < groups.size(); g++)
+        for (size_t i : groups[g]) group_of[i] = (int64_t)g;
+    if (n_groups) *n_groups = groups.size();
+    return RSN_OK;
+}
+
 // Host buffers (device == 0): small files are cut into groups and every stage runs once per group
 // (batch.cuh); files that are empty or larger than kBatchMaxFile, and device-resident batches
 // (device != 0), go through the per-file path.  Groups and leftover files are spread over
@@ -407,42 +462,9 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
         rc_local.assign(count ? count : 1, RSN_OK);
         rcs = rc_local.data();
     }
-    // groups of small files
-    size_t kGroupBytes = (size_t)16 << 20;
-    constexpr size_t kGroupFiles = 512;
-    if (const char *e = getenv("RSN_BATCH_GROUP_MIB")) {  // tuning knob
-        const long v = atol(e);
-        if (v >= 1 && v <= 1024) kGroupBytes = (size_t)v << 20;
-    }
-    // The kernels of a group size their per-file arrays for the group's LARGEST file, so a group only
-    // holds files of one size class (within a factor of two; everything below 4 KiB is one class):
-    // memory stays proportional to the bytes in the group whatever the mix of sizes.
     std::vector<std::vector<size_t>> groups;
     std::vector<size_t> singles;
-    if (!device) {
-        struct Open {
-            long group = -1;
-            size_t bytes = 0;
-        };
-        Open open[64];
-        for (size_t i = 0; i < count; i++) {
-            if (in_n[i] == 0 || in_n[i] > kBatchMaxFile || !in[i]) {
-                singles.push_back(i);
-                continue;
-            }
-            const int cls = in_n[i] < 4096 ? 11 : 63 - __builtin_clzll((unsigned long long)in_n[i]);
-            Open &o = open[cls];
-            if (o.group < 0 || o.bytes + in_n[i] > kGroupBytes || groups[(size_t)o.group].size() >= kGroupFiles) {
-                groups.emplace_back();
-                o.group = (long)groups.size() - 1;
-                o.bytes = 0;
-            }
-            groups[(size_t)o.group].push_back(i);
-            o.bytes += in_n[i];
-        }
-    } else {
-        for (size_t i = 0; i < count; i++) singles.push_back(i);
-    }
+    batch_plan(count, in, in_n, device, groups, singles);
     const size_t units = groups.size() + singles.size();
     if ((size_t)workers > units) workers = (int)(units ? units : 1);
     {
