@@ -229,7 +229,11 @@ namespace {
 // Persistent worker threads: each keeps its thread-local context (stream, arena) across batches.
 class WorkerPool {
   public:
+    // One batch at a time: job_/pending_/running_ describe a single run, and done_.wait releases
+    // mu_, so concurrent callers (the header promises re-entrancy) queue here instead of
+    // overwriting each other's job.
     void run(int workers, const std::function<void()> &job) {
+        std::lock_guard<std::mutex> serial(run_mu_);
         std::unique_lock<std::mutex> lk(mu_);
         while ((int)threads_.size() < workers) threads_.emplace_back([this] { loop(); });
         job_ = job;
@@ -259,7 +263,7 @@ class WorkerPool {
             }
         }
     }
-    std::mutex mu_;
+    std::mutex run_mu_, mu_;
     std::condition_variable cv_, done_;
     std::vector<std::thread> threads_;
     std::function<void()> job_;

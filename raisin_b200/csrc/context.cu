@@ -32,6 +32,9 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return RSN_ERR_CUDA;
 }
 
+static void release_thread_resources();
+void touch_thread_exit();
+
 static int init_ctx(int device) {
     Ctx &c = ctx();
     int count = 0;
@@ -41,8 +44,12 @@ static int init_ctx(int device) {
         RSN_CUDA(cudaGetDevice(&device));
     }
     if (device >= count) return RSN_ERR_INVALID_ARG;
+    if (c.ready && c.device == device) {
+        RSN_CUDA(cudaSetDevice(device));
+        return RSN_OK;
+    }
+    if (c.ready) release_thread_resources();  // streams, events and arena blocks belong to the old device
     RSN_CUDA(cudaSetDevice(device));
-    if (c.ready && c.device == device) return RSN_OK;
     c.device = device;
     if (!c.own_stream) RSN_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     if (!c.copy_stream) RSN_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
@@ -50,6 +57,7 @@ static int init_ctx(int device) {
         if (!e) RSN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (!c.h_scalars) RSN_CUDA(cudaHostAlloc((void **)&c.h_scalars, 64 * sizeof(uint64_t), cudaHostAllocDefault));
     c.ready = true;
+    touch_thread_exit();
     return RSN_OK;
 }
 
@@ -89,6 +97,47 @@ void arena_free_all() {
     g_arena.cur = 0;
 }
 }  // namespace
+
+// Everything the calling thread owns on its current device: streams, events, pinned scalars, arena.
+// Runs on rsn_shutdown, when the thread is re-initialised for another device, and when the thread
+// exits (cgo callers migrate over many short-lived OS threads).
+static void release_thread_resources() {
+    Ctx &c = g_ctx;
+    if (!c.ready && !c.own_stream && g_arena.blocks.empty()) return;
+    if (c.device >= 0) cudaSetDevice(c.device);
+    if (c.own_stream) {
+        cudaStreamSynchronize(c.own_stream);
+        cudaStreamDestroy(c.own_stream);
+        c.own_stream = nullptr;
+    }
+    if (c.copy_stream) {
+        cudaStreamSynchronize(c.copy_stream);
+        cudaStreamDestroy(c.copy_stream);
+        c.copy_stream = nullptr;
+    }
+    for (auto &e : c.chunk_ev)
+        if (e) {
+            cudaEventDestroy(e);
+            e = nullptr;
+        }
+    if (c.h_scalars) {
+        cudaFreeHost(c.h_scalars);
+        c.h_scalars = nullptr;
+    }
+    if (g_arena.used && g_arena.last_stream) cudaStreamSynchronize(g_arena.last_stream);
+    arena_free_all();
+    g_arena.used = false;
+    g_arena.last_stream = nullptr;
+    c.ready = false;
+    cudaGetLastError();
+}
+namespace {
+struct ThreadExit {
+    ~ThreadExit() { release_thread_resources(); }
+};
+thread_local ThreadExit g_thread_exit;
+}  // namespace
+void touch_thread_exit() { (void)&g_thread_exit; }
 
 void *arena_alloc(size_t n) {
     Arena &a = g_arena;
@@ -167,9 +216,12 @@ struct OutCache {
     struct Ent {
         size_t cap;
         cudaStream_t last;
+        int device;
     };
     std::unordered_map<void *, Ent> live;
-    std::unordered_map<size_t, std::vector<std::pair<void *, cudaStream_t>>> free_;
+    // (device, size class) -> free buffers: a buffer only ever goes back to a caller on its own device
+    std::unordered_map<uint64_t, std::vector<std::pair<void *, cudaStream_t>>> free_;
+    static uint64_t key(int device, size_t c) { return ((uint64_t)(uint32_t)device << 48) ^ (uint64_t)c; }
     size_t cached = 0;
     static constexpr size_t kMaxCached = (size_t)16 << 30;
 
@@ -181,17 +233,18 @@ struct OutCache {
     }
     void *get(size_t n, cudaStream_t s) {
         const size_t c = size_class(n);
+        const int dev = g_ctx.device;
         void *p = nullptr;
         cudaStream_t last = nullptr;
         {
             std::lock_guard<std::mutex> g(mu);
-            auto it = free_.find(c);
+            auto it = free_.find(key(dev, c));
             if (it != free_.end() && !it->second.empty()) {
                 p = it->second.back().first;
                 last = it->second.back().second;
                 it->second.pop_back();
                 cached -= c;
-                live[p] = Ent{c, s};
+                live[p] = Ent{c, s, dev};
             }
         }
         if (p) {
@@ -207,7 +260,7 @@ struct OutCache {
             }
         }
         std::lock_guard<std::mutex> g(mu);
-        live[p] = Ent{c, s};
+        live[p] = Ent{c, s, dev};
         return p;
     }
     void put(void *p, cudaStream_t s) {
@@ -218,9 +271,10 @@ struct OutCache {
             auto it = live.find(p);
             if (it == live.end()) return;  // not ours
             c = it->second.cap;
+            const int dev = it->second.device;
             live.erase(it);
             if (cached + c <= kMaxCached) {
-                free_[c].push_back({p, s});
+                free_[key(dev, c)].push_back({p, s});
                 cached += c;
                 return;
             }
@@ -459,29 +513,11 @@ extern "C" {
 int rsn_init(int device) { return rsn::init_ctx(device); }
 
 void rsn_shutdown(void) {
-    rsn::Ctx &c = rsn::ctx();
-    if (c.own_stream) {
-        cudaStreamSynchronize(c.own_stream);
-        cudaStreamDestroy(c.own_stream);
-        c.own_stream = nullptr;
-    }
-    if (c.copy_stream) {
-        cudaStreamSynchronize(c.copy_stream);
-        cudaStreamDestroy(c.copy_stream);
-        c.copy_stream = nullptr;
-    }
-    for (auto &e : c.chunk_ev)
-        if (e) {
-            cudaEventDestroy(e);
-            e = nullptr;
-        }
-    if (c.h_scalars) {
-        cudaFreeHost(c.h_scalars);
-        c.h_scalars = nullptr;
-    }
-    c.ready = false;
+    // the calling thread's own streams, events and arena ...
+    rsn::release_thread_resources();
+    // ... and the process-wide caches of free pinned and device result buffers (buffers still held by
+    // a caller stay valid and are freed when they come back)
     rsn::pinned().drain();
-    rsn::arena_free_all();
     rsn::outs().drain();
 }
 

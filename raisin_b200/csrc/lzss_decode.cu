@@ -227,7 +227,11 @@ __device__ __forceinline__ bool parse_token_fwd(const uint8_t *__restrict__ in, 
     return true;
 }
 
-enum : uint32_t { ERR_BAD_REF = 1u, FLAG_NEEDS_UNESCAPE = 2u };
+// ERR_HUGE: a token whose pointer is 2^32 or more.  Such a pointer is only valid once 4 GiB have
+// been decoded, which is beyond this build's limit anyway, so its count never enters the size sums
+// (Atoi clamps to 2^63-1: two such counts would wrap a u64 sum and defeat every later bound check).
+enum : uint32_t { ERR_BAD_REF = 1u, FLAG_NEEDS_UNESCAPE = 2u, ERR_HUGE = 4u };
+constexpr uint64_t kTileOutCap = 1ull << 33;  // per-tile size sums saturate here: >= 2^32 is unsupported
 constexpr int kMaxTok = kTile / 3 + 2;  // "<,>" is the shortest token
 
 // One tile of the compressed stream.  Threads first classify their 16 bytes (state machine from
@@ -296,6 +300,9 @@ __device__ __forceinline__ void tok_tile_body(const uint8_t *__restrict__ in, si
             if (cnt < 0 || ptr < cnt) {  // a = len - ptr: need 0 <= a <= a + cnt <= len (lzss.go:349-350)
                 flags |= ERR_BAD_REF;
                 cnt = 0;
+            } else if (ptr >= (int64_t)1 << 32) {
+                flags |= ERR_HUGE;
+                cnt = 0;
             }
         } else {
             cnt = 0;  // unterminated at end of input: dropped
@@ -309,7 +316,7 @@ __device__ __forceinline__ void tok_tile_body(const uint8_t *__restrict__ in, si
     uint64_t total;
     const uint64_t pre = block_exclusive_sum<uint64_t>(c, sm64, total);
     if (!WRITE) {
-        if (threadIdx.x == 0) tile_out[blockIdx.x] = total;
+        if (threadIdx.x == 0) tile_out[blockIdx.x] = min(total, kTileOutCap);
         if (flags) atomicOr(err, flags);
         return;
     }
@@ -636,6 +643,8 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
     const uint32_t flags = (uint32_t)c.h_scalars[1];
     if (flags & ERR_BAD_REF) return RSN_ERR_BAD_REFERENCE;
     if (sbn >= (1ull << 32)) return RSN_ERR_UNSUPPORTED;  // u32 source distances (documented limit)
+    // a pointer of 2^32 or more in a stream that decodes to less: before the start of the output
+    if (flags & ERR_HUGE) return RSN_ERR_BAD_REFERENCE;
     tr.mark("plan");
     const bool needs_unescape = (flags & FLAG_NEEDS_UNESCAPE) != 0;
     DevBuf sb, dist;  // sb becomes the result itself when no literal needs un-escaping
@@ -798,6 +807,12 @@ int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     size_t total = 0, sb_cap = 1;
     for (size_t f = 0; f < G; f++) {
         if (h[f].n && (h[f].flags & ERR_BAD_REF)) {
+            out.rc[f] = RSN_ERR_BAD_REFERENCE;
+            h[f].n = 0;
+        } else if (h[f].n && h[f].sbn >= (1ull << 32)) {  // same limit as the single-stream call
+            out.rc[f] = RSN_ERR_UNSUPPORTED;
+            h[f].n = 0;
+        } else if (h[f].n && (h[f].flags & ERR_HUGE)) {
             out.rc[f] = RSN_ERR_BAD_REFERENCE;
             h[f].n = 0;
         }

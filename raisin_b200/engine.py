@@ -88,8 +88,11 @@ def batch(files, algorithms, compress_: bool = True, workers: int = 0):
     ns = (C.c_size_t * n)(*[k[1] for k in keep])
     outs = (C.c_void_p * n)()
     out_ns = (C.c_size_t * n)()
-    rcs = (C.c_int * n)()
-    L.rsn_batch_layers(",".join(algorithms).encode(), 1 if compress_ else 0, n, ins, ns, outs, out_ns, rcs, workers, 0)
+    sentinel = -1000  # no code the library returns: "the call never reached this file"
+    rcs = (C.c_int * n)(*([sentinel] * n))
+    rc = L.rsn_batch_layers(",".join(algorithms).encode(), 1 if compress_ else 0, n, ins, ns, outs, out_ns, rcs, workers, 0)
+    if rc != 0 and all(r == sentinel for r in rcs):
+        raise _lib.RaisinPanic(rc, L.rsn_strerror(rc).decode())  # failed before any per-file work (unknown layer, no device, ...)
     res = []
     for i in range(n):
         if rcs[i] != 0:

@@ -94,3 +94,47 @@ def huffman_cases():
     c["skewed"] = (b"e" * 4000 + b"t" * 2000 + b"a" * 1000 + b"o" * 500 + b"i" * 250 + b"n" * 125 + b"s" * 60 +
                    b"h" * 30 + b"r" * 15 + b"d" * 7 + b"l" * 3 + b"u" * 2 + b"z")
     return c
+
+
+# ---- reference-recorded artefacts ----------------------------------------------------------
+# /root/reference/ai/data.json holds results the reference's own engine.BenchmarkFile produced
+# with the `lzss` engine of that era (the iterative lz.Compress, window 4096) on files that can
+# be rebuilt offline.  Each record: what the Go code measured on its own output, i.e. pins for
+# lz.Compress + lz.Decompress that do not come from our restatement.
+#   compressed_ratio  = float32(len(compressed)) / float32(len(input)) * 100   (engine.go:409)
+#   compressed_entropy = float32(natural-log Shannon entropy of the compressed bytes' histogram)
+#   lossless          = DeepEqual(input, Decompress(Compress(input)))           (engine.go:408)
+
+def entropy_nat(b: bytes) -> float:
+    if not b:
+        return 0.0
+    h = np.bincount(np.frombuffer(b, dtype=np.uint8), minlength=256).astype(np.float64)
+    p = h[h > 0] / len(b)
+    return float(-(p * np.log(p)).sum())
+
+
+def pi_txt() -> bytes:
+    """Canterbury pi.txt (first 10^6 digits of pi), rebuilt by tests/tools/make_pi_fixture.py."""
+    import lzma
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pi_1e6.xz"), "rb") as f:
+        return lzma.decompress(f.read())
+
+
+def reference_recorded():
+    """name -> (input bytes, recorded input entropy, compressed_ratio, compressed_entropy, lossless,
+    data.json line of the lzss record)."""
+    alpha = (b"abcdefghijklmnopqrstuvwxyz" * 3847)[:100000]
+    return {
+        "aaa.txt": (b"a" * 100000, 0.0, 0.4000000059604645, 2.591623306274414, True, 2016),
+        "alphabet.txt": (alpha, 3.2580965336217447, 100.0, 3.25809645652771, True, 2158),
+        "a.txt": (b"a", 0.0, 100.0, 0.0, True, 2726),
+        "pi.txt": (pi_txt(), 2.3025823330123467, 100.0, 2.3026533126831055, False, 3365),
+    }
+
+
+def recorded_result(data: bytes, comp: bytes, back: bytes):
+    """What engine.BenchmarkFile of that era would have recorded for these buffers."""
+    ratio = float(np.float32(len(comp)) / np.float32(len(data)) * np.float32(100))
+    return ratio, float(np.float32(entropy_nat(comp))), back == data

@@ -107,9 +107,18 @@ def test_batch_bad_streams_fail_alone(rsn):
     bad = b"abc<9,4>def"          # pointer before the start of the output (lzss.go:349)
     got = rsn.engine.batch([lz, bad, lz], ["lzss"], False, workers=1)
     assert got[0] == ok and got[2] == ok and got[1] is None
+    # counts that Atoi clamps to 2^63-1 must not wrap the group's size sums into a neighbour's bytes
+    huge = b"abc" + b"<9223372036854775807,9223372036854775807>" * 2 + b"xyz"
+    got = rsn.engine.batch([lz, huge, lz, b"ab<4294967296,0>", lz], ["lzss"], False, workers=1)
+    assert got[0] == ok and got[2] == ok and got[4] == ok and got[1] is None and got[3] is None
     hf = rsn.huffman.Compress(ok)
     got = rsn.engine.batch([hf, b"no separator here", hf[: len(hf) // 2], hf], ["huffman"], False, workers=1)
     assert got[0] == ok and got[3] == ok and got[1] is None
+
+
+def test_batch_call_level_failure_raises(rsn):
+    with pytest.raises(rsn.RaisinPanic):
+        rsn.engine.batch([b"abc"], ["lzss", "nosuchlayer"], True)
 
 
 def test_batch_config4_shape(rsn, oracle):
@@ -122,3 +131,31 @@ def test_batch_config4_shape(rsn, oracle):
     back = rsn.engine.batch(got, algos, False)
     for j in range(len(files)):
         assert back[j] == rsn.engine.decompress(got[j], algos)
+
+
+def test_batch_concurrent_callers(rsn):
+    """rsn_batch_layers from several OS threads at once (the worker pool's run() must not
+    let a second caller overwrite the first caller's job)."""
+    import threading
+
+    algos = ["lzss", "huffman"]
+    sets = [[synth.batch_file(40 * k + j, 30000 + 777 * j) for j in range(24)] for k in range(4)]
+    want = [[rsn.engine.compress(f, algos) for f in fs] for fs in sets]
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(3):
+                got = rsn.engine.batch(sets[k], algos, True, workers=2)
+                assert got == want[k]
+                back = rsn.engine.batch(got, algos, False, workers=2)
+                assert all(b is not None for b in back)
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(sets))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

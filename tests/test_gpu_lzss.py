@@ -110,7 +110,11 @@ def test_decompress_arbitrary_streams(rsn, oracle):
     """lz.Decompress semantics on streams no compressor produced (junk tokens, signs, overflow)."""
     samples = [b"abc<2,2>", b"abc<3,3><6,6>", b"<,>", b"x<abc,>y", b"ab<+2,+1>", b"ab<2,1", b"ab<2", b"a<b<c,d>e",
                b"abc<1,2>", b"abc<4,1>", b"abc<-1,0>", b"abc<99999999999999999999,0>", b"ab<2,1>>,<1,1>",
-               b"\\<1,1>", b"ab<02,01>", b"ab<2,-1>", b"ab<2,1,1>", b"", b"<", b">", b",", b"abc\\", b"\xff\\\xff\\\\"]
+               b"\\<1,1>", b"ab<02,01>", b"ab<2,-1>", b"ab<2,1,1>",
+               # Atoi clamps to 2^63-1: counts that would wrap a 64-bit size sum (ADVICE r1)
+               b"abc<9223372036854775807,9223372036854775807><9223372036854775807,9223372036854775807>xyz",
+               b"ab<99999999999,0>cd", b"ab<4294967296,0>", b"ab<4294967295,0>",
+               b"ab<18446744073709551615,18446744073709551615>" * 2 + b"zz", b"", b"<", b">", b",", b"abc\\", b"\xff\\\xff\\\\"]
     for s in samples:
         try:
             want = oracle.lzss_decompress(s)
@@ -154,6 +158,35 @@ def test_one_mib_text(rsn, oracle):
     got = rsn.lz.CompressAsync(data)
     assert got == want
     assert rsn.lz.Decompress(got) == data
+
+
+@pytest.mark.parametrize("name", ["aaa.txt", "alphabet.txt", "a.txt", "pi.txt"])
+def test_reference_recorded_results(rsn, oracle, name):
+    """The CUDA path against numbers the stock Go code recorded about its own output
+    (/root/reference/ai/data.json, see cases.reference_recorded): compressed size as a float32
+    ratio, histogram entropy of the compressed bytes, and the lossless flag of
+    Decompress(Compress(x)) — no restatement of ours in between."""
+    data, _ent_in, ratio, ent_c, lossless, _line = cases.reference_recorded()[name]
+    comp = rsn.lz.Compress(data, False, 4096)
+    try:
+        back = rsn.lz.Decompress(comp, False)
+    except rsn.RaisinPanic:
+        back = None
+    assert cases.recorded_result(data, comp, back) == (ratio, ent_c, lossless)
+    assert comp == oracle.lzss_compress_iter(data, 4096)
+
+
+def test_config2_full_size_equals_oracle(rsn, oracle):
+    """BASELINE configs[1] at its full size: the 64 MiB text stream, variant A, W = 4096 — the
+    compressed bytes equal the oracle's (fast search mode, all host threads; ~20 s), and the
+    decoder returns the input."""
+    data = synth.text(64 << 20, 2)
+    want = oracle.lzss_compress_async(data, 4096, threads=os.cpu_count() or 1)
+    got = rsn.lz.CompressAsync(data)
+    assert len(got) == len(want) and sha(got) == sha(want)
+    assert got == want
+    assert rsn.lz.Decompress(got) == data
+    assert rsn.lz.Decompress(want) == oracle.lzss_decompress(want) == data
 
 
 def test_full_size_roundtrip_properties(rsn):

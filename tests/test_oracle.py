@@ -81,6 +81,35 @@ def test_reference_sam_i_am(oracle):
     assert gl.huff_Compress(sam, order=sorted) == h
 
 
+# ---- artefacts the reference itself recorded (ai/data.json) --------------------------------
+
+@pytest.mark.parametrize("name", ["aaa.txt", "alphabet.txt", "a.txt", "pi.txt"])
+def test_reference_recorded_results(oracle, name):
+    """Outputs of the stock Go code on offline-reconstructible files, as recorded by the
+    reference's own benchmark run (/root/reference/ai/data.json, `"engine": "lzss"` records; that
+    build's lzss engine was lz.Compress with window 4096).  They pin, from the reference side:
+    aaa.txt -> exactly 400 bytes whose histogram entropy is 2.5916233 nat (every token of the
+    doubling sequence and the window-relative pointer of lzss.go:256 enter that histogram);
+    alphabet.txt -> unchanged (the stride-2 start search of lzss.go:423-433 never finds an even
+    period); pi.txt -> same length, different bytes, NOT lossless (tokens as long as their match are
+    emitted, lzss.go:272 `<=`, with pointers that are wrong beyond the window, lzss.go:256)."""
+    data, ent_in, ratio, ent_c, lossless, _line = cases.reference_recorded()[name]
+    assert abs(cases.entropy_nat(data) - ent_in) < 1e-14  # the rebuilt input is the recorded file
+    comp = oracle.lzss_compress_iter(data, 4096)
+    try:
+        back = oracle.lzss_decompress(comp)
+    except oracle.OracleError:
+        back = None
+    got = cases.recorded_result(data, comp, back)
+    assert got == (ratio, ent_c, lossless), (name, got)
+    if name == "aaa.txt":
+        assert len(comp) == 400
+    if name == "pi.txt":
+        assert len(comp) == 1_000_000 and comp != data
+    if len(data) <= 100000 and name != "alphabet.txt":
+        assert gl.Compress(data, 4096) == comp  # literal transcription agrees on the pinned inputs
+
+
 # ---- golden fixtures --------------------------------------------------------------------
 
 @pytest.mark.parametrize("name", sorted(GOLDEN["lzss"]))
@@ -168,7 +197,11 @@ def test_decoder_on_arbitrary_streams(oracle):
     """lz.Decompress on streams that no compressor produced: junk tokens, signs, overflow."""
     samples = [b"abc<2,2>", b"abc<3,3><6,6>", b"<,>", b"x<abc,>y", b"ab<+2,+1>", b"ab<2,1", b"ab<2", b"a<b<c,d>e",
                b"abc<1,2>", b"abc<4,1>", b"abc<-1,0>", b"abc<99999999999999999999,0>", b"ab<2,1>>,<1,1>",
-               b"\\<1,1>", b"ab<02,01>", b"ab<2,-1>", b"ab<2,1,1>"]
+               b"\\<1,1>", b"ab<02,01>", b"ab<2,-1>", b"ab<2,1,1>",
+               # Atoi clamps to 2^63-1: counts that would wrap a 64-bit size sum (ADVICE r1)
+               b"abc<9223372036854775807,9223372036854775807><9223372036854775807,9223372036854775807>xyz",
+               b"ab<99999999999,0>cd", b"ab<4294967296,0>", b"ab<4294967295,0>",
+               b"ab<18446744073709551615,18446744073709551615>" * 2 + b"zz"]
     for s in samples:
         try:
             want = gl.Decompress(s)
