@@ -1,21 +1,31 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the LZSS (+Huffman) hot path.
+"""bench.py — headline benchmark of the LZSS + Huffman hot path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload lzss|layered]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload batch|stream]
 
-One "step" = one pass of the hot path over one batch: compress then decompress the whole
-stream (the reference's own timed region, engine/engine.go:379-406).  The N=1 workload is
-BASELINE.json configs[1]: lzss compress+decompress of a 64 MiB synthetic text stream with the
-reference's window (4096) and min-match (-1, "smart") parameters.  For N>1 every rank handles
-its own independent 64 MiB stream (north_star: batches of independent files partitioned across
-GPUs; no data-path collective) — weak scaling.
+Default workload = BASELINE.json configs[3], the configuration the metric ("lzss+huffman
+encode/decode GB/s (1/2/4/8 B200)") is quoted on: a batch of 4096 x 256 KiB synthetic files (kind =
+j mod 3: text / logs / random bytes, seed 1000 + j), layered `lzss,huffman`, the files partitioned
+round-robin over the N ranks (one process per GPU, no data-path collective; FIXED total, i.e.
+strong scaling).  One "step" = one pass of the hot path over the batch: compress every file, then
+decompress every result (the reference's own timed region, engine/engine.go:379-406, per file).
 
-Prints ONE JSON line on rank 0.  `value` = uncompressed bytes through compress+decompress per
-second, inputs resident in HBM; `e2e` = the same through the C-ABI host-buffer calls with
-pinned host buffers (H2D and D2H inside the timed region).
+Prints ONE JSON line on rank 0:
+  value     uncompressed bytes of the whole batch / max-over-ranks step time, files resident in HBM
+            before the timed region and results left in HBM (rsn_batch_layers, device buffers)
+  e2e       the same through rsn_batch_layers with pinned HOST buffers in and out
+  roofline  the dominant kernel of the step (per-kernel CUDA-event times from the library's own
+            launch timer, measured live in an extra pass), algorithmic bytes per SURVEY 8(d)
+  parity    GPU output bytes compared with the CPU oracle on a sample of the same files
+  cpu_baseline   the oracle port of the Go reference on a bounded sample (rank 0, N = 1 only)
+  stream_c2 (N = 1) BASELINE configs[1]: lzss compress+decompress of one 64 MiB text stream
+
+`--workload stream` makes configs[1] the headline instead (same keys).
+`--impl reference` times the CPU port of the reference on the host cores (rank 0 only).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import statistics
@@ -23,13 +33,19 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ProcessPoolExecutor, ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_BYTES = 64 << 20
+N_STREAM = 64 << 20
 WINDOW = 4096
-METRIC = "lzss compress+decompress GB/s (uncompressed bytes / (encode+decode time)), bit-exact vs reference semantics"
+FILE_BYTES = 262144
+N_FILES = 4096
+ALGOS = b"lzss,huffman"
+METRIC = ("lzss,huffman compress+decompress GB/s over a batch of independent files (uncompressed bytes / "
+          "(encode+decode time)), bit-exact vs reference semantics")
+METRIC_STREAM = "lzss compress+decompress GB/s (uncompressed bytes / (encode+decode time)), bit-exact vs reference semantics"
 
 
 def peaks():
@@ -42,21 +58,12 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def k2_traffic(n):
-    """DRAM bytes of one K2 launch from the committed ncu --set full capture (per launch)."""
-    p = os.path.join(ROOT, "profiles", "r1_k2_ncu_full.md")
+def committed_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture, or None."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
-        rd = wr = None
-        for line in open(p):
-            parts = line.split()
-            if line.startswith("dram__bytes_read.sum"):
-                rd = float(parts[1]) * (1e6 if parts[2].startswith("Mbyte") else 1e9 if parts[2].startswith("Gbyte") else 1e3 if parts[2].startswith("Kbyte") else 1)
-            if line.startswith("dram__bytes_write.sum"):
-                wr = float(parts[1]) * (1e6 if parts[2].startswith("Mbyte") else 1e9 if parts[2].startswith("Gbyte") else 1e3 if parts[2].startswith("Kbyte") else 1)
-        if rd is None or wr is None:
-            return None
-        return int((rd + wr) * n / N_BYTES)
-    except OSError:
+        return json.load(open(p)).get(kernel)
+    except (OSError, ValueError):
         return None
 
 
@@ -113,145 +120,571 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------ reference arm
+def _gen_file(j):
+    from raisin_b200 import synth
+
+    return synth.batch_file(j, FILE_BYTES)
+
+
+def make_files(indices):
+    """Synthetic files of config 4 (deterministic per index), generated on a few processes."""
+    procs = min(16, os.cpu_count() or 1, max(1, len(indices) // 64))
+    if procs <= 1:
+        return [_gen_file(j) for j in indices]
+    with ProcessPoolExecutor(procs) as ex:
+        return list(ex.map(_gen_file, indices, chunksize=32))
+
+
+def batch_config(world, n_files):
+    return {"workload": f"batch of {n_files} x 256 KiB synthetic files (text/logs/random by j mod 3), layered "
+                        "lzss,huffman, compress + decompress (BASELINE configs[3])",
+            "files": n_files, "file_bytes": FILE_BYTES, "window": WINDOW, "algorithms": "lzss,huffman",
+            "parallelism": f"files partitioned round-robin over {world} rank(s), no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------ CPU oracle legs
+
+
+def oracle_batch(files, literal, threads):
+    """lzss,huffman compress + decompress of every file with the CPU oracle; files run side by side
+    on `threads` host threads (ctypes releases the GIL).  Returns (seconds, compressed, decoded)."""
+    from oracle import pyoracle as po
+
+    def one(f):
+        lz = po.lzss_compress_async(f, WINDOW, literal=literal, threads=1)
+        hf = po.huff_compress(lz)
+        try:
+            back = po.lzss_decompress(po.huff_decompress(hf))
+        except po.OracleError:
+            back = None
+        return hf, back
+
+    po.lib()
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(one, files))
+    dt = time.perf_counter() - t0
+    return dt, [r[0] for r in res], [r[1] for r in res]
 
 
 def run_reference(args, rank, world):
-    """The reference's CPU implementation of the path, timed on this box's host cores.  The Go
-    reference cannot be built here (no Go toolchain), so this is the oracle port in literal mode
-    (per position, repeated leftmost-substring search over the window, all host threads), on a
-    bounded sample of the same workload."""
+    """The reference's CPU implementation of the path on this box's host cores.  The Go code cannot
+    be built here (no Go toolchain in the image), so this is the oracle port in literal mode (per
+    position, repeated leftmost-substring search over the window — the structure of lzss.go:156-184;
+    Huffman with the reference's heap and linear-time packing), files side by side on all host
+    threads, on a bounded sample of the same workload per step."""
     if rank != 0:
         return
-    from oracle import pyoracle as po
-    from raisin_b200 import synth
-
     cores = os.cpu_count() or 1
-    sample_n = 2 << 20
-    data = synth.text(N_BYTES if args.full_reference else sample_n, 2)[:sample_n]
-    times = []
-    for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        comp = po.lzss_compress_async(data, WINDOW, literal=True, threads=cores)
-        back = po.lzss_decompress(comp)
-        dt = time.perf_counter() - t0
-        assert back == data
-        if it >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    gbs = sample_n / (ms * 1e-3) / 1e9
+    if args.workload == "stream":
+        from oracle import pyoracle as po
+        from raisin_b200 import synth
+
+        sample_n = 2 << 20
+        data = synth.text(sample_n, 2)
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            comp = po.lzss_compress_async(data, WINDOW, literal=True, threads=cores)
+            back = po.lzss_decompress(comp)
+            dt = time.perf_counter() - t0
+            assert back == data
+            if it >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * sum(times) / len(times)
+        gbs = sample_n / (ms * 1e-3) / 1e9
+        metric, config = METRIC_STREAM, stream_config(1)
+        sample = f"first {sample_n >> 20} MiB of the 64 MiB text stream per step"
+    else:
+        sample_files = max(3, min(args.ref_files, args.files))
+        idx = list(range(sample_files))
+        files = make_files(idx)
+        total = sum(len(f) for f in files)
+        times = []
+        for it in range(args.warmup + args.steps):
+            dt, _, _ = oracle_batch(files, True, cores)
+            if it >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * sum(times) / len(times)
+        gbs = total / (ms * 1e-3) / 1e9
+        metric, config = METRIC, batch_config(world, args.files)
+        sample = f"files 0..{sample_files - 1} of the batch ({total >> 20} MiB) per step"
     line = {
-        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "lzss compress+decompress, 64 MiB synthetic text stream, window 4096 (BASELINE configs[1])",
-                   "window": WINDOW, "stream_bytes": N_BYTES},
+        "impl": "reference", "metric": metric, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "batch" else "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
-                         "sample": f"first {sample_n >> 20} MiB of the 64 MiB text stream per step; C port of the Go "
-                                   "reference (no Go toolchain in this image), literal per-position search, "
-                                   f"{cores} threads"},
+                         "sample": sample + "; C port of the Go reference (no Go toolchain in this image), literal "
+                                            f"per-position search, {cores} threads"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------ batch workload
+# ------------------------------------------------------------------------------------------ helpers (GPU)
+
+
+def kernel_report(lib):
+    n = lib.rsn_kernel_timing_report(None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib.rsn_kernel_timing_report(buf, n + 1)
+    rows = []
+    for ln in buf.value.decode().splitlines():
+        name, cnt, ms = ln.rsplit(" ", 2)
+        rows.append((name, int(cnt), float(ms)))
+    return rows
+
+
+STAGE_OF = [  # kernel-name prefix -> stage whose algorithmic bytes it is charged with (SURVEY 8(d))
+    ("kb_match", "lzss_compress"), ("k_match", "lzss_compress"), ("kb_escape", "lzss_compress"),
+    ("k_escape", "lzss_compress"), ("kb_parse", "lzss_compress"), ("k_parse", "lzss_compress"),
+    ("kb_emit", "lzss_compress"), ("k_emit", "lzss_compress"), ("kb_lz_", "lzss_compress"), ("k_lz_", "lzss_compress"),
+    ("kb_tok", "lzss_decompress"), ("k_tok", "lzss_decompress"), ("k_resolve", "lzss_decompress"),
+    ("kb_unesc", "lzss_decompress"), ("k_unesc", "lzss_decompress"),
+    ("kb_huff_tree", "huffman_tree"), ("kb_rune", "huffman_compress"), ("k_rune", "huffman_compress"),
+    ("kb_enc", "huffman_compress"), ("k_enc", "huffman_compress"), ("kb_hist", "huffman_compress"),
+    ("kb_hdec", "huffman_decompress"), ("k_hdec", "huffman_decompress"),
+]
+
+
+def stage_of(kernel):
+    for pre, st in STAGE_OF:
+        if kernel.startswith(pre):
+            return st
+    return "other"
+
+
+# ------------------------------------------------------------------------------------------ stream workload (c2)
+
+
+def stream_config(world):
+    return {"workload": "lzss compress+decompress, 64 MiB synthetic text stream, window 4096 (BASELINE configs[1])",
+            "window": WINDOW, "stream_bytes": N_STREAM, "streams_per_gpu": 1,
+            "parallelism": f"independent streams x{world}", "l2": "flushed between timed iterations (256 MiB write)"}
+
+
+def measure_stream(args, torch, rsn, lib, rank, steps, warmup, with_e2e=True, with_oracle=True):
+    """BASELINE configs[1] on this rank's GPU.  Returns a dict of numbers (ms, bytes, parity)."""
+    from raisin_b200 import synth
+
+    n = args.bytes
+    data = synth.text(n, 2 + rank)
+    stream = torch.cuda.Stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    res = {"n": n}
+
+    def free(*ptrs):
+        for p in ptrs:
+            lib.rsn_dev_free(p, sptr)
+
+    def dev_step():
+        out, out_n, back, back_n = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+        rsn._lib.check(lib.rsn_dev_lzss_compress(d_in.data_ptr(), n, WINDOW, 0, C.byref(out), C.byref(out_n), sptr))
+        rsn._lib.check(lib.rsn_dev_lzss_decompress(out, out_n.value, C.byref(back), C.byref(back_n), sptr))
+        return out, out_n.value, back, back_n.value
+
+    with torch.cuda.stream(stream):
+        # what is being timed, checked: the compressed stream and the round trip, downloaded once
+        out, c_bytes, back, back_n = dev_step()
+        assert back_n == n
+        h_back = (C.c_uint8 * n)()
+        rsn._lib.check(lib.rsn_dev_download(back, n, h_back, sptr))
+        assert bytes(h_back) == data, "device round trip differs"
+        h_comp = (C.c_uint8 * c_bytes)()
+        rsn._lib.check(lib.rsn_dev_download(out, c_bytes, h_comp, sptr))
+        gpu_comp = bytes(h_comp)
+        free(out, back)
+        del h_back, h_comp
+        res["c"] = c_bytes
+
+        def timed(fn, k, w):
+            for _ in range(w):
+                fn()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+            torch.cuda.synchronize()
+            for a, b in ev:
+                flush.fill_(1)  # L2 flush between timed iterations (outside the events)
+                a.record(stream)
+                fn()
+                b.record(stream)
+            torch.cuda.synchronize()
+            return statistics.mean(a.elapsed_time(b) for a, b in ev)
+
+        def both():
+            o, _, b, _ = dev_step()
+            free(o, b)
+
+        lib.rsn_reset_kernel_launches()
+        res["ms"] = timed(both, steps, warmup)
+        res["launches_per_step"] = int(lib.rsn_kernel_launches()) // (steps + warmup)
+        keep = {}
+
+        def enc_only():
+            o, on = C.c_void_p(), C.c_size_t()
+            rsn._lib.check(lib.rsn_dev_lzss_compress(d_in.data_ptr(), n, WINDOW, 0, C.byref(o), C.byref(on), sptr))
+            if "c" in keep:
+                lib.rsn_dev_free(keep["c"], sptr)
+            keep["c"], keep["cn"] = o, on.value
+
+        def dec_only():
+            o, on = C.c_void_p(), C.c_size_t()
+            rsn._lib.check(lib.rsn_dev_lzss_decompress(keep["c"], keep["cn"], C.byref(o), C.byref(on), sptr))
+            lib.rsn_dev_free(o, sptr)
+
+        sub = max(3, steps // 2)
+        res["enc_ms"] = timed(enc_only, sub, 1)
+        res["dec_ms"] = timed(dec_only, sub, 1)
+        hk = {}
+
+        def henc_only():
+            o, on = C.c_void_p(), C.c_size_t()
+            rsn._lib.check(lib.rsn_dev_huff_compress(keep["c"], keep["cn"], C.byref(o), C.byref(on), sptr))
+            if "h" in hk:
+                lib.rsn_dev_free(hk["h"], sptr)
+            hk["h"], hk["hn"] = o, on.value
+
+        def hdec_only():
+            o, on = C.c_void_p(), C.c_size_t()
+            rsn._lib.check(lib.rsn_dev_huff_decompress(hk["h"], hk["hn"], 0, C.byref(o), C.byref(on), sptr))
+            lib.rsn_dev_free(o, sptr)
+
+        res["henc_ms"] = timed(henc_only, sub, 2)
+        res["hdec_ms"] = timed(hdec_only, sub, 2)
+        res["hn"] = hk["hn"]
+
+        # per-kernel device times of one compress + decompress, from the library's launch timer
+        lib.rsn_kernel_timing(1)
+        flush.fill_(1)
+        both()
+        res["kernels"] = kernel_report(lib)
+        lib.rsn_kernel_timing(0)
+        free(keep["c"], hk["h"])
+
+    if with_e2e:
+        h_in = lib.rsn_host_alloc(n)
+        C.memmove(h_in, data, n)
+        e2e_ms = []
+        for it in range(2 + max(3, steps // 2)):
+            o, on = C.POINTER(C.c_uint8)(), C.c_size_t()
+            b, bn = C.POINTER(C.c_uint8)(), C.c_size_t()
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rsn._lib.check(lib.rsn_lzss_compress(h_in, n, WINDOW, 0, C.byref(o), C.byref(on)))
+            rsn._lib.check(lib.rsn_lzss_decompress(o, on.value, C.byref(b), C.byref(bn)))
+            dt = (time.perf_counter() - t0) * 1e3
+            if it == 0:
+                assert C.string_at(b, bn.value) == data, "host round trip differs"
+                assert C.string_at(o, on.value) == gpu_comp, "host-buffer call and device call disagree"
+            res["h2d"], res["d2h"] = n + on.value, on.value + bn.value
+            lib.rsn_free(o)
+            lib.rsn_free(b)
+            if it >= 2:
+                e2e_ms.append(dt)
+        lib.rsn_host_free(h_in)
+        res["e2e_ms"] = statistics.mean(e2e_ms)
+
+    res["parity"] = {"bytes": c_bytes, "sha256": hashlib.sha256(gpu_comp).hexdigest(), "equal": None,
+                     "checked_against": "not run"}
+    if with_oracle:
+        from oracle import pyoracle as po
+
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        comp = po.lzss_compress_async(data, WINDOW, literal=True, threads=cores)
+        backb = po.lzss_decompress(comp)
+        dt = time.perf_counter() - t0
+        assert backb == data
+        res["parity"] = {"bytes": len(comp), "sha256": hashlib.sha256(comp).hexdigest(), "equal": comp == gpu_comp,
+                         "checked_against": "CPU oracle (literal mode) over the whole stream"}
+        res["cpu"] = {"value": n / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                      "sample": f"the whole {n >> 20} MiB stream, compress+decompress, C port of the Go reference in "
+                                f"literal mode, {cores} threads, {dt:.1f} s"}
+    del d_in, flush
+    torch.cuda.empty_cache()
+    return res
+
+
+def stream_summary(r, world=1):
+    n = r["n"]
+    out = {"config": stream_config(world), "value": world * n / (r["ms"] * 1e-3) / 1e9, "unit": "GB/s",
+           "ms_per_step": r["ms"], "encode_GBps": world * n / (r["enc_ms"] * 1e-3) / 1e9,
+           "decode_GBps": world * n / (r["dec_ms"] * 1e-3) / 1e9, "compressed_bytes": r["c"],
+           "huffman_layer": {"input_bytes": r["c"], "output_bytes": r["hn"],
+                             "encode_GBps": world * r["c"] / (r["henc_ms"] * 1e-3) / 1e9,
+                             "decode_GBps": world * r["c"] / (r["hdec_ms"] * 1e-3) / 1e9},
+           "gpu_launches_per_step": r["launches_per_step"], "parity": r["parity"]}
+    if "e2e_ms" in r:
+        out["e2e"] = {"value": world * n / (r["e2e_ms"] * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": r["h2d"],
+                      "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["e2e_ms"]}
+    return out
+
+
+def stream_roofline(r):
+    """The dominant kernel of one compress + decompress of the stream."""
+    peak, peak_src = peaks()
+    name, cnt, ms = r["kernels"][0]
+    n, c = r["n"], r["c"]
+    stage_bytes = {"lzss_compress": n + c, "lzss_decompress": c + n}
+    st = stage_of(name)
+    algo = stage_bytes.get(st, n + c)
+    per_launch_ms = ms / cnt
+    achieved = algo / cnt / (per_launch_ms * 1e-3) / 1e9
+    tot = sum(k[2] for k in r["kernels"])
+    return {"bound": "hbm", "kernel": name, "stage": st, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": committed_traffic(name), "peak_source": peak_src,
+            "launches": cnt, "kernel_ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": algo / cnt,
+            "share_of_kernel_time": ms / tot if tot else None,
+            "kernels": [{"name": k[0], "launches": k[1], "ms": round(k[2], 4)} for k in r["kernels"][:10]],
+            "note": "match search is integer/shared-memory bound, not HBM bound; see DESIGN.md"}
+
+
+# ------------------------------------------------------------------------------------------ batch workload (c4)
 
 
 def run_batch(args, rank, local_rank, world):
-    """BASELINE configs[3] shape: independent 256 KiB files (kind j mod 3, seed 1000 + j), layered
-    lzss,huffman, files partitioned round-robin over ranks; every rank runs `--files` of them through
-    rsn_batch_layers (host buffers in and out).  One step = compress all + decompress all."""
     import torch
     import torch.distributed as dist
 
+    from raisin_b200 import parallel
+
+    mine = parallel.partition_files(args.files, world, rank)
+    files = make_files(mine)  # before CUDA is initialised (the generator pool forks)
+
     import raisin_b200 as rsn
-    from raisin_b200 import parallel, synth
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = rsn._lib.lib()
     rsn._lib.check(lib.rsn_init(local_rank))
-    mine = parallel.partition_files(args.files * world, world, rank)
-    files = [synth.batch_file(j) for j in mine]
-    total = sum(len(f) for f in files)
     n = len(files)
-    keep = [rsn._lib._as_ptr(f) for f in files]
-    ins = (C.c_void_p * n)(*[k[0] for k in keep])
-    ns = (C.c_size_t * n)(*[k[1] for k in keep])
+    total = sum(len(f) for f in files)
+    total_all = args.files * FILE_BYTES
 
-    def step(check=False):
+    # ---- inputs resident in HBM: one buffer, files at 256 KiB strides
+    blob = b"".join(files)
+    d_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+    offs = [0]
+    for f in files:
+        offs.append(offs[-1] + len(f))
+    d_ins = (C.c_void_p * n)(*[d_blob.data_ptr() + o for o in offs[:-1]])
+    ns = (C.c_size_t * n)(*[len(f) for f in files])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    del blob
+
+    def dev_pass(keep=False, algos=ALGOS):
         outs, out_ns, rcs = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
-        rsn._lib.check(lib.rsn_batch_layers(b"lzss,huffman", 1, n, ins, ns, outs, out_ns, rcs, args.workers, 0))
-        b_outs, b_ns = (C.c_void_p * n)(), (C.c_size_t * n)()
-        rsn._lib.check(lib.rsn_batch_layers(b"lzss,huffman", 0, n, outs, out_ns, b_outs, b_ns, rcs, args.workers, 0))
-        csum = sum(out_ns)
-        lossless = 0
-        if check:
-            lossless = sum(C.string_at(b_outs[i], b_ns[i]) == files[i] for i in range(n))
-        for i in range(n):
-            lib.rsn_free(outs[i])
-            lib.rsn_free(b_outs[i])
-        return csum, lossless
+        rsn._lib.check(lib.rsn_batch_layers(algos, 1, n, d_ins, ns, outs, out_ns, rcs, args.workers, 1))
+        b_outs, b_ns, rcs2 = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        rsn._lib.check(lib.rsn_batch_layers(algos, 0, n, outs, out_ns, b_outs, b_ns, rcs2, args.workers, 1))
+        if keep:
+            return outs, out_ns, b_outs, b_ns
+        lib.rsn_dev_free_many(outs, n, None)
+        lib.rsn_dev_free_many(b_outs, n, None)
+        return sum(out_ns)
 
-    csum, lossless = step(check=True)
-    for _ in range(max(args.warmup, 3) - 1):
-        step()
+    def download(ptrs, sizes, which):
+        res = []
+        for i in which:
+            h = (C.c_uint8 * max(1, sizes[i]))()
+            rsn._lib.check(lib.rsn_dev_download(ptrs[i], sizes[i], h, None))
+            res.append(bytes(h)[:sizes[i]])
+        return res
+
+    # ---- parity of what is being timed (untimed): every compressed file hashed, a sample compared
+    # with the CPU oracle byte for byte, both directions
+    outs, out_ns, b_outs, b_ns = dev_pass(keep=True)
+    csum = sum(out_ns)
+    comp_all = download(outs, out_ns, range(n))
+    sha_all = hashlib.sha256(b"".join(comp_all)).hexdigest()
+    sample = sorted(set(range(0, n, max(1, n // args.parity_files))))[:args.parity_files] if rank == 0 else []
+    back_sample = download(b_outs, b_ns, sample)
+    lossless = 0
+    if rank == 0:
+        back_all = download(b_outs, b_ns, range(n)) if n <= 1024 else None
+        if back_all is not None:
+            lossless = sum(back_all[i] == files[i] for i in range(n))
+            del back_all
+    lib.rsn_dev_free_many(outs, n, None)
+    lib.rsn_dev_free_many(b_outs, n, None)
+    parity = None
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        dt, want_c, want_b = oracle_batch([files[i] for i in sample], True, cores)
+        eq_c = sum(comp_all[i] == w for i, w in zip(sample, want_c))
+        eq_b = sum(b == w for b, w in zip(back_sample, want_b))
+        sb = sum(len(files[i]) for i in sample)
+        parity = {"files_checked": len(sample), "compressed_equal": eq_c, "decompressed_equal": eq_b,
+                  "equal": eq_c == len(sample) and eq_b == len(sample),
+                  "bytes": sum(len(w) for w in want_c),
+                  "sha256": hashlib.sha256(b"".join(want_c)).hexdigest(),
+                  "gpu_sha256_same_files": hashlib.sha256(b"".join(comp_all[i] for i in sample)).hexdigest(),
+                  "checked_against": "CPU oracle (literal mode), lzss,huffman compress and decompress, files "
+                                     f"{sample[0]}..{sample[-1]} step {sample[1] - sample[0] if len(sample) > 1 else 1} of rank 0's share",
+                  "sha256_all_compressed_rank0": sha_all}
+        if world == 1:
+            cpu = {"value": sb / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                   "sample": f"{len(sample)} files of the batch ({sb >> 20} MiB), lzss,huffman compress+decompress, C "
+                             f"port of the Go reference in literal mode, files side by side on {cores} threads, {dt:.1f} s"}
+    del comp_all, back_sample
+
+    # ---- timed: device resident
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        dev_pass()
     lib.rsn_reset_kernel_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    # this workload is host-side launch heavy: poll the driver once a second, not ten times
-    sampler = ClockSampler(local_rank, interval_ms=1000)
+    sampler = ClockSampler(local_rank, interval_ms=500)
     sampler.start()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    wall = []
+    for a, b in ev:
+        flush.fill_(1)  # L2 flush between timed iterations, outside the events
+        torch.cuda.synchronize()
+        a.record()
+        t0 = time.perf_counter()
+        dev_pass()
+        b.record()
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t0) * 1e3)
     clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
     launches = int(lib.rsn_kernel_launches())
+    ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    wall_ms = statistics.mean(wall)
+
+    # ---- e2e: pinned host buffers in and out
+    h_ptrs = []
+    for f in files:
+        p = lib.rsn_host_alloc(len(f))
+        C.memmove(p, f, len(f))
+        h_ptrs.append(p)
+    h_ins = (C.c_void_p * n)(*h_ptrs)
+
+    def host_pass():
+        outs, out_ns, rcs = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        rsn._lib.check(lib.rsn_batch_layers(ALGOS, 1, n, h_ins, ns, outs, out_ns, rcs, args.workers, 0))
+        b_outs, b_ns, rcs2 = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        rsn._lib.check(lib.rsn_batch_layers(ALGOS, 0, n, outs, out_ns, b_outs, b_ns, rcs2, args.workers, 0))
+        c, d = sum(out_ns), sum(b_ns)
+        lib.rsn_free_many(outs, n)
+        lib.rsn_free_many(b_outs, n)
+        return c, d
+
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(2):
+        host_pass()
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_list = []
+    for _ in range(e2e_steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hc, hd = host_pass()
+        e2e_list.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = statistics.mean(e2e_list)
+    for p in h_ptrs:
+        lib.rsn_host_free(p)
+
+    # ---- per-kernel device times of one pass (one worker: kernels run alone on the GPU), and the
+    # intermediate (LZSS) size the stage byte counts need
+    outs, out_ns, rcs = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+    rsn._lib.check(lib.rsn_batch_layers(b"lzss", 1, n, d_ins, ns, outs, out_ns, rcs, args.workers, 1))
+    c_lz = sum(out_ns)
+    lib.rsn_dev_free_many(outs, n, None)
+    saved_workers = args.workers
+    args.workers = 1
+    dev_pass()
+    lib.rsn_kernel_timing(1)
+    flush.fill_(1)
+    torch.cuda.synchronize()
+    dev_pass()
+    kernels = kernel_report(lib)
+    lib.rsn_kernel_timing(0)
+    args.workers = saved_workers
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+        ms, e2e_ms, wall_ms = t.tolist()
+        t = torch.tensor([float(launches), float(csum)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        launches, csum_all = int(t[0].item()), int(t[1].item())
+    else:
+        csum_all = csum
+
+    line = None
     if rank == 0:
-        gbs = world * total / (ms * 1e-3) / 1e9
-        print(json.dumps({
-            "metric": "lzss,huffman compress+decompress GB/s over a batch of independent files (host buffers)",
-            "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": f"batch of {n} x 256 KiB files per GPU (BASELINE configs[3] shape), lzss,huffman",
-                       "files_per_gpu": n, "bytes_per_gpu": total, "workers": args.workers},
-            "compressed_bytes_per_gpu": csum, "lossless_files": lossless, "of_files": n,
+        peak, peak_src = peaks()
+        back_lz = total  # lz.Decompress output of this rank's files: as many bytes as went in (sizes, not content)
+        stage_bytes = {"lzss_compress": total + c_lz, "lzss_decompress": c_lz + back_lz,
+                       "huffman_compress": 2 * c_lz + csum, "huffman_decompress": csum + c_lz, "huffman_tree": csum}
+        name, cnt, kms = kernels[0]
+        st = stage_of(name)
+        algo = stage_bytes.get(st, total)
+        achieved = algo / (kms * 1e-3) / 1e9
+        ktot = sum(k[2] for k in kernels)
+        line = {
+            "metric": METRIC, "value": total_all / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": dict(batch_config(world, args.files), workers=args.workers,
+                                                               l2="flushed between timed iterations (256 MiB write)"),
+            "timing": "CUDA events on the default stream around each step (the C-ABI calls return when the step's "
+                      "work has finished), max over ranks; wall clock beside it",
+            "wall_ms_per_step": wall_ms,
+            "compressed_bytes": csum_all, "lzss_stage_bytes_rank0": c_lz, "lossless_files_rank0": lossless,
+            "files_rank0": n,
+            "e2e": {"value": total_all / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": total + hc,
+                    "d2h_bytes_per_step": hc + hd, "ms_per_step": e2e_ms,
+                    "note": "rsn_batch_layers with pinned host buffers in and out; bytes are per rank"},
             "gpu_launches": launches, "clocks": clocks,
-            "timing": "host wall clock around the C-ABI calls (host buffers in and out), max over ranks",
-            "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": total + csum, "d2h_bytes_per_step": total + csum},
-        }), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+            "roofline": {"bound": "hbm", "kernel": name, "stage": st, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": committed_traffic(name), "peak_source": peak_src,
+                         "launches": cnt, "kernel_ms_per_launch": kms / cnt,
+                         "algorithmic_bytes_per_launch": algo / cnt,
+                         "algorithmic_bytes": f"{st}: bytes in + bytes out of that stage over rank 0's {n} files (SURVEY 8(d)), "
+                                              "divided over the kernel's launches",
+                         "share_of_kernel_time": kms / ktot if ktot else None,
+                         "kernels": [{"name": k[0], "launches": k[1], "ms": round(k[2], 4)} for k in kernels[:12]],
+                         "measured": "cudaEvent pairs around every launch on its own stream (rsn_kernel_timing), one extra "
+                                     "pass with one worker so kernels run alone"},
+        }
+        if parity:
+            line["parity"] = parity
+        if cpu:
+            line["cpu_baseline"] = cpu
+    return line, (torch, dist, rsn, lib)
 
 
-# ------------------------------------------------------------------------------------------ our arm
+# ------------------------------------------------------------------------------------------ main
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bytes", type=int, default=N_BYTES)
-    ap.add_argument("--full-reference", action="store_true")
+    ap.add_argument("--workload", default="batch", choices=["batch", "stream"],
+                    help="batch: BASELINE configs[3] (default, the metric's own workload); stream: configs[1]")
+    ap.add_argument("--files", type=int, default=N_FILES, help="batch workload: files in the whole batch (256 KiB each)")
+    ap.add_argument("--bytes", type=int, default=N_STREAM, help="stream workload: bytes per stream")
+    ap.add_argument("--workers", type=int, default=0, help="host threads/streams per rank for the batch call (0 = default)")
+    ap.add_argument("--parity-files", type=int, default=48, help="files compared with the CPU oracle (rank 0)")
+    ap.add_argument("--ref-files", type=int, default=24, help="--impl reference: files per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="stream", choices=["stream", "batch"],
-                    help="stream: BASELINE configs[1] (default, the headline); batch: configs[3] shape")
-    ap.add_argument("--files", type=int, default=512, help="batch workload: files per GPU (256 KiB each)")
-    ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--no-stream", action="store_true", help="skip the configs[1] side measurement at N = 1")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -260,215 +693,55 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
     if args.workload == "batch":
-        run_batch(args, rank, local_rank, world)
+        line, (torch, dist, rsn, lib) = run_batch(args, rank, local_rank, world)
+        if rank == 0 and world == 1 and not args.no_stream:
+            r = measure_stream(args, torch, rsn, lib, 0, max(3, args.steps), 3, with_oracle=not args.no_cpu_baseline)
+            line["stream_c2"] = stream_summary(r)
+            line["stream_c2"]["roofline"] = stream_roofline(r)
+            if "cpu" in r:
+                line["stream_c2"]["cpu_baseline"] = r["cpu"]
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return
 
+    # ---- stream workload as the headline (weak scaling: one independent 64 MiB stream per rank)
     import torch
     import torch.distributed as dist
 
     import raisin_b200 as rsn
-    from raisin_b200 import synth
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = rsn._lib.lib()
     rsn._lib.check(lib.rsn_init(local_rank))
-    n = args.bytes
-    data = synth.text(n, 2 + rank)  # rank r: its own independent stream
-    stream = torch.cuda.Stream()  # a real (non-default) stream: the library launches on exactly this one
-    torch.cuda.set_stream(stream)
-    sptr = C.c_void_p(stream.cuda_stream)
-    assert stream.cuda_stream != 0
-
-    # ---- device-resident input
-    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    def dev_step():
-        out = C.c_void_p()
-        out_n = C.c_size_t()
-        rsn._lib.check(lib.rsn_dev_lzss_compress(d_in.data_ptr(), n, WINDOW, 0, C.byref(out), C.byref(out_n), sptr))
-        back = C.c_void_p()
-        back_n = C.c_size_t()
-        rsn._lib.check(lib.rsn_dev_lzss_decompress(out, out_n.value, C.byref(back), C.byref(back_n), sptr))
-        return out, out_n.value, back, back_n.value
-
-    def free(*ptrs):
-        for p in ptrs:
-            lib.rsn_dev_free(p, sptr)
-
-    # correctness of what is being timed: round trip on device
-    out, c_bytes, back, back_n = dev_step()
-    assert back_n == n
-    h_back = (C.c_uint8 * n)()
-    rsn._lib.check(lib.rsn_dev_download(back, n, h_back, sptr))
-    assert bytes(h_back) == data, "device round trip differs"
-    free(out, back)
-    del h_back
-
-    def timed(fn, steps, warmup, after_warmup=None):
-        for _ in range(warmup):
-            r = fn()
-            if r:
-                free(r[0], r[2])
-        if after_warmup:
-            after_warmup()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        for a, b in ev:
-            flush.fill_(1)  # L2 flush between timed iterations (outside the events)
-            a.record(stream)
-            r = fn()
-            b.record(stream)
-            if r:
-                free(r[0], r[2])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        return [a.elapsed_time(b) for a, b in ev]
-
+    if world > 1:
+        dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_list = timed(dev_step, args.steps, args.warmup, after_warmup=lib.rsn_reset_kernel_launches)
-    launches = int(lib.rsn_kernel_launches())
+    r = measure_stream(args, torch, rsn, lib, rank, args.steps, max(3, args.warmup),
+                       with_oracle=(rank == 0 and not args.no_cpu_baseline))
     clocks = sampler.stop()
-    ms = sum(ms_list) / len(ms_list)
-
-    # ---- separate encode / decode timings (device resident)
-    keep = {}
-
-    def enc_only():
-        o = C.c_void_p()
-        on = C.c_size_t()
-        rsn._lib.check(lib.rsn_dev_lzss_compress(d_in.data_ptr(), n, WINDOW, 0, C.byref(o), C.byref(on), sptr))
-        if "c" in keep:
-            lib.rsn_dev_free(keep["c"], sptr)
-        keep["c"], keep["cn"] = o, on.value
-        return None
-
-    enc_ms = statistics.mean(timed(enc_only, max(3, args.steps // 2), 1))
-
-    def dec_only():
-        o = C.c_void_p()
-        on = C.c_size_t()
-        rsn._lib.check(lib.rsn_dev_lzss_decompress(keep["c"], keep["cn"], C.byref(o), C.byref(on), sptr))
-        lib.rsn_dev_free(o, sptr)
-        return None
-
-    dec_ms = statistics.mean(timed(dec_only, max(3, args.steps // 2), 1))
-
-    # ---- Huffman layer on the same stream (BASELINE configs[0]/[2] use it): encode/decode of the
-    # LZSS output, device resident
-    hk = {}
-
-    def henc_only():
-        o = C.c_void_p()
-        on = C.c_size_t()
-        rsn._lib.check(lib.rsn_dev_huff_compress(keep["c"], keep["cn"], C.byref(o), C.byref(on), sptr))
-        if "h" in hk:
-            lib.rsn_dev_free(hk["h"], sptr)
-        hk["h"], hk["hn"] = o, on.value
-        return None
-
-    henc_ms = statistics.mean(timed(henc_only, max(3, args.steps // 2), 2))
-
-    def hdec_only():
-        o = C.c_void_p()
-        on = C.c_size_t()
-        rsn._lib.check(lib.rsn_dev_huff_decompress(hk["h"], hk["hn"], 0, C.byref(o), C.byref(on), sptr))
-        lib.rsn_dev_free(o, sptr)
-        return None
-
-    hdec_ms = statistics.mean(timed(hdec_only, max(3, args.steps // 2), 2))
-
-    # ---- dominant kernel (K2 match search) alone, CUDA events on its launch stream
-    # the text stream has no '<', '\\' or 0xFF bytes, so the escaped buffer equals the raw one
-    d_packed = torch.empty(n, dtype=torch.int32, device="cuda")
-
-    def k2_only():
-        rsn._lib.check(lib.rsn_dev_lzss_match(d_in.data_ptr(), n, WINDOW, d_packed.data_ptr(), sptr))
-        return None
-
-    k2_ms = statistics.mean(timed(k2_only, max(3, args.steps // 2), 1))
-
-    # ---- e2e through the host-buffer C ABI, pinned host memory in and out
-    h_in = lib.rsn_host_alloc(n)
-    C.memmove(h_in, data, n)
-    e2e_ms = []
-    for it in range(2 + max(3, args.steps // 2)):
-        o = C.POINTER(C.c_uint8)()
-        on = C.c_size_t()
-        b = C.POINTER(C.c_uint8)()
-        bn = C.c_size_t()
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        rsn._lib.check(lib.rsn_lzss_compress(h_in, n, WINDOW, 0, C.byref(o), C.byref(on)))
-        rsn._lib.check(lib.rsn_lzss_decompress(o, on.value, C.byref(b), C.byref(bn)))
-        dt = (time.perf_counter() - t0) * 1e3
-        if it == 0:
-            assert C.string_at(b, bn.value) == data, "host round trip differs"
-        h2d, d2h = n + on.value, on.value + bn.value
-        lib.rsn_free(o)
-        lib.rsn_free(b)
-        if it >= 2:
-            e2e_ms.append(dt)
-    lib.rsn_host_free(h_in)
-    e2e = sum(e2e_ms) / len(e2e_ms)
-
-    # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e, enc_ms, dec_ms, k2_ms, henc_ms, hdec_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([r["ms"], r["e2e_ms"], r["enc_ms"], r["dec_ms"], r["henc_ms"], r["hdec_ms"]], dtype=torch.float64,
+                         device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e, enc_ms, dec_ms, k2_ms, henc_ms, hdec_ms = t.tolist()
-
-    peak, peak_src = peaks()
-    algo_bytes_k2 = n + keep["cn"]  # LZSS compress = n + c per stream; one K2 launch = one stream
-    achieved = algo_bytes_k2 / (k2_ms * 1e-3) / 1e9
-    line = {
-        "metric": METRIC, "value": world * n / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "lzss compress+decompress, 64 MiB synthetic text stream, window 4096 (BASELINE configs[1])",
-                   "window": WINDOW, "stream_bytes": n, "streams_per_gpu": 1, "parallelism": f"independent streams x{world}",
-                   "l2": "flushed between timed iterations (256 MiB write)"},
-        "encode_GBps": world * n / (enc_ms * 1e-3) / 1e9, "decode_GBps": world * n / (dec_ms * 1e-3) / 1e9,
-        "compressed_bytes": keep["cn"],
-        "huffman_layer": {"input_bytes": keep["cn"], "output_bytes": hk["hn"],
-                          "encode_GBps": world * keep["cn"] / (henc_ms * 1e-3) / 1e9,
-                          "decode_GBps": world * keep["cn"] / (hdec_ms * 1e-3) / 1e9,
-                          "layered_encode_GBps": world * n / ((enc_ms + henc_ms) * 1e-3) / 1e9,
-                          "layered_decode_GBps": world * n / ((dec_ms + hdec_ms) * 1e-3) / 1e9},
-        "e2e": {"value": world * n / (e2e * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e},
-        "gpu_launches": launches,
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "lzss match search (K2)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": k2_traffic(n), "peak_source": peak_src,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_match_tile launch on the "
-                                       "64 MiB stream, profiles/r1_k2_ncu_full.md (scaled by n if --bytes differs)",
-                     "kernel_ms": k2_ms, "algorithmic_bytes": algo_bytes_k2,
-                     "note": "K2 is integer/shared-memory bound, not HBM bound; see DESIGN.md"},
-    }
-    if rank == 0 and not args.no_cpu_baseline:
-        from oracle import pyoracle as po
-
-        cores = os.cpu_count() or 1
-        sample_n = min(len(data), 64 << 20)  # ~11 s of CPU work on 16 cores
-        sample = data[:sample_n]
-        t0 = time.perf_counter()
-        comp = po.lzss_compress_async(sample, WINDOW, literal=True, threads=cores)
-        backb = po.lzss_decompress(comp)
-        dt = time.perf_counter() - t0
-        assert backb == sample
-        line["cpu_baseline"] = {"value": sample_n / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
-                                "sample": f"first {sample_n >> 20} MiB of the stream, compress+decompress, C port of "
-                                          f"the Go reference in literal mode, {cores} threads, {dt:.1f} s"}
+        r["ms"], r["e2e_ms"], r["enc_ms"], r["dec_ms"], r["henc_ms"], r["hdec_ms"] = t.tolist()
     if rank == 0:
+        s = stream_summary(r, world)
+        line = {"metric": METRIC_STREAM, "value": s["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": s["config"],
+                "encode_GBps": s["encode_GBps"], "decode_GBps": s["decode_GBps"], "compressed_bytes": r["c"],
+                "huffman_layer": s["huffman_layer"], "e2e": s["e2e"],
+                "gpu_launches": r["launches_per_step"] * args.steps * world, "clocks": clocks,
+                "roofline": stream_roofline(r), "parity": r["parity"]}
+        if "cpu" in r:
+            line["cpu_baseline"] = r["cpu"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

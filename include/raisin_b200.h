@@ -56,6 +56,9 @@ const char *rsn_strerror(int rc);
 const char *rsn_last_cuda_error(void);
 /* Release a buffer returned through an `out` parameter of the host-buffer API. */
 void rsn_free(void *p);
+/* The results of a batch call in one go (NULL entries are skipped). */
+void rsn_free_many(void *const *ptrs, size_t count);
+void rsn_dev_free_many(void *const *d_ptrs, size_t count, void *stream);
 /* Pinned host allocation helpers (optional; any host pointer is accepted as input). */
 void *rsn_host_alloc(size_t n);
 void rsn_host_free(void *p);
@@ -92,13 +95,16 @@ int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, u
  * Batches of independent files (BASELINE configs[3]; what engine.BenchmarkSuite's per-file loop does,
  * engine.go:208-262): file i is compressed (or decompressed) with the layer list exactly as
  * rsn_compress_layers would.  Host buffers (device == 0): files of up to 4 MiB are cut into groups
- * of about 16 MiB and every kernel of a stage runs once per group (the file index is a grid
+ * of about 64 MiB and every kernel of a stage runs once per group (the file index is a grid
  * dimension), so a small file costs no kernel launches or synchronisations of its own; groups, and
  * the files that go one by one (empty, larger than 4 MiB), are spread over `workers` host threads
  * (0 = default), each with its own CUDA stream.  out[i]/out_n[i] receive library-owned buffers
  * (rsn_free each); rcs[i] (optional) the per-file code: a file the reference would panic on fails
  * alone.  Returns RSN_OK or the first failing file's code.  With device != 0 the in/out pointers
- * are device pointers (release with rsn_dev_free(p, NULL)) and files go one by one.
+ * are device pointers on the calling thread's device: inputs are used in place (grouped like host
+ * files when 16-byte aligned, otherwise one by one), every result is its own device buffer
+ * (release with rsn_dev_free(p, NULL)); nothing crosses PCIe except sizes — and, when the first
+ * layer to undo is "huffman", a host copy of the streams for the header parser.
  */
 int rsn_batch_layers(const char *algorithms, int compress, size_t count, const uint8_t *const *in, const size_t *in_n,
                      uint8_t **out, size_t *out_n, int *rcs, int workers, int device);
@@ -106,7 +112,7 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
  * The grouping rsn_batch_layers applies to host-buffer files of these sizes (host logic only; needs
  * no device): group_of[i] = index of the group file i travels in, or -1 for the per-file path
  * (empty files, files above 4 MiB).  A group holds files of one size class (within a factor of
- * two of each other; everything below 4 KiB is one class), at most 512 files and about 16 MiB.
+ * two of each other; everything below 4 KiB is one class), at most 2048 files and about 64 MiB.
  */
 int rsn_batch_plan(size_t count, const size_t *in_n, int64_t *group_of, size_t *n_groups);
 
@@ -151,6 +157,14 @@ int rsn_dev_lzss_escape(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
 /* Number of kernels this library has launched (from any thread) since the last reset. */
 uint64_t rsn_kernel_launches(void);
 void rsn_reset_kernel_launches(void);
+/*
+ * Per-kernel device timing for benchmarks: rsn_kernel_timing(1) makes every kernel launch of the
+ * library record two CUDA events on its own stream (and clears earlier records); 0 turns it off.
+ * rsn_kernel_timing_report writes one line per kernel name, "<name> <launches> <total ms>\n", most
+ * expensive first, into buf (NUL terminated, truncated to cap) and returns the full length.
+ */
+void rsn_kernel_timing(int enable);
+size_t rsn_kernel_timing_report(char *buf, size_t cap);
 /* "raisin_b200 <version> sm_100a" */
 const char *rsn_version(void);
 

@@ -13,12 +13,12 @@ SO_PATH = os.path.join(_HERE, "libraisin_b200.so")
 
 # every symbol include/raisin_b200.h declares
 EXPORTS = [
-    "rsn_init", "rsn_shutdown", "rsn_strerror", "rsn_last_cuda_error", "rsn_free", "rsn_host_alloc",
+    "rsn_init", "rsn_shutdown", "rsn_strerror", "rsn_last_cuda_error", "rsn_free", "rsn_free_many", "rsn_dev_free_many", "rsn_host_alloc",
     "rsn_host_free", "rsn_lzss_compress", "rsn_lzss_decompress", "rsn_huff_compress", "rsn_huff_decompress",
     "rsn_compress_layers", "rsn_decompress_layers", "rsn_batch_layers", "rsn_batch_plan", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
     "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_free", "rsn_dev_download", "rsn_dev_upload",
     "rsn_dev_lzss_match", "rsn_dev_lzss_emit", "rsn_dev_lzss_escape",
-    "rsn_kernel_launches", "rsn_reset_kernel_launches", "rsn_version",
+    "rsn_kernel_launches", "rsn_reset_kernel_launches", "rsn_kernel_timing", "rsn_kernel_timing_report", "rsn_version",
 ]
 
 RSN_LZSS_ASYNC = 0
@@ -58,6 +58,10 @@ def lib():
     L.rsn_last_cuda_error.restype = C.c_char_p
     L.rsn_free.argtypes = [C.c_void_p]
     L.rsn_free.restype = None
+    L.rsn_free_many.argtypes = [C.c_void_p, C.c_size_t]
+    L.rsn_free_many.restype = None
+    L.rsn_dev_free_many.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    L.rsn_dev_free_many.restype = None
     L.rsn_host_alloc.argtypes = [C.c_size_t]
     L.rsn_host_alloc.restype = C.c_void_p
     L.rsn_host_free.argtypes = [C.c_void_p]
@@ -94,6 +98,10 @@ def lib():
     L.rsn_kernel_launches.restype = C.c_uint64
     L.rsn_reset_kernel_launches.argtypes = []
     L.rsn_reset_kernel_launches.restype = None
+    L.rsn_kernel_timing.argtypes = [C.c_int]
+    L.rsn_kernel_timing.restype = None
+    L.rsn_kernel_timing_report.argtypes = [C.c_char_p, C.c_size_t]
+    L.rsn_kernel_timing_report.restype = C.c_size_t
     L.rsn_version.argtypes = []
     L.rsn_version.restype = C.c_char_p
     _lib = L

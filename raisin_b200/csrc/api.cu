@@ -284,22 +284,26 @@ extern "C" {
 namespace rsn {
 // Which files of a batch travel together.  groups[g] lists the files of group g (every kernel of a
 // stage runs once per group), `singles` the files that go through the per-file path: empty files,
-// files above kBatchMaxFile, null inputs, and everything in a device-resident batch.
+// files above kBatchMaxFile, null inputs, and device-resident files that are not 16-byte aligned.
 // The kernels of a group size their per-file arrays for the group's LARGEST file, so a group only
 // holds files of one size class (within a factor of two; everything below 4 KiB is one class):
 // memory stays proportional to the bytes in the group whatever the mix of sizes.  `in` may be null
 // (planning only).
 void batch_plan(size_t count, const uint8_t *const *in, const size_t *in_n, int device,
                 std::vector<std::vector<size_t>> &groups, std::vector<size_t> &singles) {
-    size_t group_bytes = (size_t)16 << 20;
-    constexpr size_t kGroupFiles = 512;
-    if (const char *e = getenv("RSN_BATCH_GROUP_MIB")) {  // tuning knob
+    // 64 MiB groups: the per-group costs that do not shrink with the group (the serial heap replay of
+    // the Huffman tree kernel, ~4 ms for a file of random bytes, and a handful of host
+    // synchronisations per stage) are paid 16 times per GiB instead of 64 (2048 config-4 files:
+    // 3.6 GB/s with 16 MiB groups, 4.4 GB/s with 64 MiB, 8 workers)
+    size_t group_bytes = (size_t)64 << 20;
+    size_t kGroupFiles = 2048;
+    if (const char *e = getenv("RSN_BATCH_GROUP_MIB")) {  // tuning knobs
         const long v = atol(e);
-        if (v >= 1 && v <= 1024) group_bytes = (size_t)v << 20;
+        if (v >= 1 && v <= 4096) group_bytes = (size_t)v << 20;
     }
-    if (device) {
-        for (size_t i = 0; i < count; i++) singles.push_back(i);
-        return;
+    if (const char *e = getenv("RSN_BATCH_GROUP_FILES")) {
+        const long v = atol(e);
+        if (v >= 1 && v <= 32768) kGroupFiles = (size_t)v;
     }
     struct Open {
         long group = -1;
@@ -307,7 +311,8 @@ void batch_plan(size_t count, const uint8_t *const *in, const size_t *in_n, int 
     };
     Open open[64];
     for (size_t i = 0; i < count; i++) {
-        if (in_n[i] == 0 || in_n[i] > kBatchMaxFile || (in && !in[i])) {
+        if (in_n[i] == 0 || in_n[i] > kBatchMaxFile || (in && !in[i]) ||
+            (device && in && (reinterpret_cast<uintptr_t>(in[i]) & 15))) {  // the grouped kernels load 16 bytes at a time
             singles.push_back(i);
             continue;
         }
@@ -361,9 +366,35 @@ int stage_batched(Algo a, bool compress, const BatchIO &in, const uint8_t *const
     return RSN_ERR_UNSUPPORTED;
 }
 
-// The files idx[0..G) of a batch through every layer; results to library-owned host buffers.
+// results of a device-resident group: every file from the group's buffer into its own buffer
+struct CopyJob {
+    const uint8_t *src;
+    uint8_t *dst;
+    uint64_t n;
+};
+__global__ void __launch_bounds__(256) kb_copy_out(const CopyJob *__restrict__ jobs) {
+    const CopyJob j = jobs[blockIdx.y];
+    const size_t chunk = (size_t)256 * 16 * 4;  // 16 KiB per CTA
+    const size_t lo = (size_t)blockIdx.x * chunk;
+    if (lo >= j.n) return;
+    const size_t hi = min((size_t)j.n, lo + chunk);
+    if (((reinterpret_cast<uintptr_t>(j.src) | reinterpret_cast<uintptr_t>(j.dst)) & 15) == 0) {
+        const size_t v_lo = lo / 16, v_hi = hi / 16;
+        const uint4 *sv = reinterpret_cast<const uint4 *>(j.src);
+        uint4 *dv = reinterpret_cast<uint4 *>(j.dst);
+        for (size_t v = v_lo + threadIdx.x; v < v_hi; v += blockDim.x) dv[v] = __ldg(sv + v);
+        for (size_t b = v_hi * 16 + threadIdx.x; b < hi; b += blockDim.x) j.dst[b] = j.src[b];
+    } else {
+        for (size_t b = lo + threadIdx.x; b < hi; b += blockDim.x) j.dst[b] = j.src[b];
+    }
+}
+
+// The files idx[0..G) of a batch through every layer.  Host mode: inputs are uploaded into one
+// buffer and results land in library-owned pinned host buffers.  Device mode: inputs are used in
+// place and every result gets its own device buffer (rsn_dev_free).
 int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector<size_t> &idx,
-                const uint8_t *const *in, const size_t *in_n, uint8_t **out, size_t *out_n, int *rcs, cudaStream_t s) {
+                const uint8_t *const *in, const size_t *in_n, uint8_t **out, size_t *out_n, int *rcs, bool device,
+                cudaStream_t s) {
     const size_t G = idx.size();
     ArenaScope scope(s);
     Trace tr("batch", s);
@@ -372,22 +403,44 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
     size_t total = 0;
     for (size_t f = 0; f < G; f++) total += (in_n[idx[f]] + 64 + 255) & ~(size_t)255;
     DevBuf d;
-    RSN_TRY(d.alloc(total + 256, s));
     std::vector<const uint8_t *> h_in(G);
+    uint8_t *h_stage = nullptr;  // device mode: host copy of the streams for the Huffman header parser
+    struct StageFree {
+        uint8_t *&p;
+        ~StageFree() {
+            if (p) rsn_free(p);
+        }
+    } stage_free{h_stage};
+    const Algo first = compress ? algos.front() : algos.back();
+    if (!device) {
+        RSN_TRY(d.alloc(total + 256, s));
+    } else if (!compress && first == ALGO_HUFFMAN) {
+        h_stage = (uint8_t *)host_out_alloc(total + 256);
+        if (!h_stage) return RSN_ERR_NOMEM;
+    }
     size_t off = 0;
     for (size_t f = 0; f < G; f++) {
         const size_t i = idx[f];
-        cur.ptr[f] = d.as<uint8_t>() + off;
         cur.n[f] = in_n[i];
-        h_in[f] = in[i];
-        if (in_n[i]) RSN_CUDA(cudaMemcpyAsync(d.as<uint8_t>() + off, in[i], in_n[i], cudaMemcpyHostToDevice, s));
+        if (!device) {
+            cur.ptr[f] = d.as<uint8_t>() + off;
+            h_in[f] = in[i];
+            if (in_n[i]) RSN_CUDA(cudaMemcpyAsync(d.as<uint8_t>() + off, in[i], in_n[i], cudaMemcpyHostToDevice, s));
+        } else {
+            cur.ptr[f] = in[i];
+            h_in[f] = h_stage ? h_stage + off : nullptr;
+            if (h_stage && in_n[i])
+                RSN_CUDA(cudaMemcpyAsync(h_stage + off, in[i], in_n[i], cudaMemcpyDeviceToHost, s));
+        }
         off += (in_n[i] + 64 + 255) & ~(size_t)255;
     }
-    tr.mark("h2d");
+    if (h_stage) RSN_CUDA(cudaStreamSynchronize(s));
+    const bool have_host = !device || h_stage != nullptr;
+    tr.mark(device ? "stage" : "h2d");
     const size_t k = algos.size();
     for (size_t step = 0; step < k; step++) {
         const Algo a = compress ? algos[step] : algos[k - 1 - step];
-        const uint8_t *const *hp = step == 0 ? h_in.data() : nullptr;  // host copies exist for the first stage only
+        const uint8_t *const *hp = step == 0 && have_host ? h_in.data() : nullptr;  // host copies: first stage only
         BatchIO next;
         int rc = stage_batched(a, compress, cur, hp, next, s);
         if (rc == RSN_ERR_UNSUPPORTED) {
@@ -401,6 +454,38 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
         }
         cur = std::move(next);
         tr.mark(a == ALGO_LZSS ? "lzss stage" : "huffman stage");
+    }
+    if (device) {  // every file into its own result buffer, one launch for the group
+        std::vector<CopyJob> jobs(G);
+        size_t cap = 0;
+        int rc = RSN_OK;
+        for (size_t f = 0; f < G; f++) {
+            const size_t i = idx[f];
+            out[i] = nullptr;
+            out_n[i] = 0;
+            jobs[f] = CopyJob{nullptr, nullptr, 0};
+            if (rcs) rcs[i] = cur.rc[f];
+            if (cur.rc[f] != RSN_OK) continue;
+            uint8_t *p = (uint8_t *)out_alloc(cur.n[f] + 16, s);
+            if (!p) {
+                if (rcs) rcs[i] = RSN_ERR_NOMEM;
+                rc = RSN_ERR_NOMEM;
+                continue;
+            }
+            jobs[f] = CopyJob{cur.ptr[f], p, cur.n[f]};
+            cap = std::max<size_t>(cap, cur.n[f]);
+            out[i] = p;
+            out_n[i] = cur.n[f];
+        }
+        DevBuf dj;
+        RSN_TRY(dj.alloc(G * sizeof(CopyJob), s));
+        RSN_CUDA(cudaMemcpyAsync(dj.p, jobs.data(), G * sizeof(CopyJob), cudaMemcpyHostToDevice, s));
+        if (cap) RSN_LAUNCH(kb_copy_out, dim3((unsigned)div_up(cap, 16384), (unsigned)G), 256, 0, s, dj.as<CopyJob>());
+        cudaError_t e = cudaStreamSynchronize(s);  // `jobs` is read by the copy above
+        if (e != cudaSuccess) rc = cuda_fail(e, "batch copy-out sync", __FILE__, __LINE__);
+        cur.release(s);
+        tr.mark("copy out");
+        return rc;
     }
     // device -> host: all copies queued, one synchronisation
     int rc = RSN_OK;
@@ -492,10 +577,11 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
             if (u >= units) break;
             if (u < groups.size()) {
                 const std::vector<size_t> &idx = groups[u];
-                const int rc = batch_group(algos, compress != 0, idx, in, in_n, out, out_n, rcs, s);
+                const int rc = batch_group(algos, compress != 0, idx, in, in_n, out, out_n, rcs, device != 0, s);
                 if (rc != RSN_OK) {  // the whole group failed (device error, out of memory)
                     for (size_t i : idx) {
-                        if (out[i]) rsn_free(out[i]);
+                        if (out[i] && device) out_free(out[i], s);
+                        else if (out[i]) rsn_free(out[i]);
                         out[i] = nullptr;
                         out_n[i] = 0;
                         if (rcs) rcs[i] = rc;

@@ -40,10 +40,17 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         if (_rc != RSN_OK) return _rc; \
     } while (0)
 
-// kernel launch with launch counting and error check
+// Per-kernel device timing (rsn_kernel_timing): when enabled, every launch is bracketed by two CUDA
+// events on its own stream; rsn_kernel_timing_report() sums the durations per kernel name.
+int ktime_begin(const char *name, cudaStream_t s);  // -1 when timing is off
+void ktime_end(int idx, cudaStream_t s);
+
+// kernel launch with launch counting, optional event timing and error check
 #define RSN_LAUNCH(kernel, grid, block, smem, stream, ...)                   \
     do {                                                                     \
+        const int _kt = ::rsn::ktime_begin(#kernel, (stream));               \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);          \
+        if (_kt >= 0) ::rsn::ktime_end(_kt, (stream));                       \
         ::rsn::count_launch();                                               \
         RSN_CUDA(cudaGetLastError());                                        \
     } while (0)

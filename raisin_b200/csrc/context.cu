@@ -1,7 +1,9 @@
 // context.cu — per-thread context, error plumbing, buffer pools, spine scan, library lifetime.
 #include "common.cuh"
 
+#include <algorithm>
 #include <atomic>
+#include <string>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +22,47 @@ static std::atomic<uint64_t> g_launches{0};  // all threads (batch workers launc
 void count_launch() {
     g_ctx.launches++;
     g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+// ----------------------------------------------------------------------------- per-kernel timing
+
+namespace {
+struct KTimer {
+    std::atomic<bool> on{false};
+    std::mutex mu;
+    struct Rec {
+        const char *name;
+        cudaEvent_t a, b;
+    };
+    std::vector<Rec> recs;
+};
+KTimer &ktimer() {
+    static KTimer *t = new KTimer();
+    return *t;
+}
+}  // namespace
+
+int ktime_begin(const char *name, cudaStream_t s) {
+    KTimer &t = ktimer();
+    if (!t.on.load(std::memory_order_relaxed)) return -1;
+    KTimer::Rec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    cudaEventRecord(r.a, s);
+    std::lock_guard<std::mutex> g(t.mu);
+    t.recs.push_back(r);
+    return (int)t.recs.size() - 1;
+}
+void ktime_end(int idx, cudaStream_t s) {
+    KTimer &t = ktimer();
+    cudaEvent_t b;
+    {
+        std::lock_guard<std::mutex> g(t.mu);
+        b = t.recs[(size_t)idx].b;
+    }
+    cudaEventRecord(b, s);
 }
 
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
@@ -105,6 +148,10 @@ static void release_thread_resources() {
     Ctx &c = g_ctx;
     if (!c.ready && !c.own_stream && g_arena.blocks.empty()) return;
     if (c.device >= 0) cudaSetDevice(c.device);
+    // work that still reads arena memory may be queued on a caller's stream (or on own_stream, which
+    // is destroyed below): wait for it first
+    if (g_arena.used && g_arena.last_stream && g_arena.last_stream != c.own_stream)
+        cudaStreamSynchronize(g_arena.last_stream);
     if (c.own_stream) {
         cudaStreamSynchronize(c.own_stream);
         cudaStreamDestroy(c.own_stream);
@@ -124,7 +171,6 @@ static void release_thread_resources() {
         cudaFreeHost(c.h_scalars);
         c.h_scalars = nullptr;
     }
-    if (g_arena.used && g_arena.last_stream) cudaStreamSynchronize(g_arena.last_stream);
     arena_free_all();
     g_arena.used = false;
     g_arena.last_stream = nullptr;
@@ -551,6 +597,65 @@ void rsn_dev_free(void *d_ptr, void *stream) {
     if (!d_ptr) return;
     cudaStream_t s = stream ? (cudaStream_t)stream : rsn::ctx().own_stream;
     rsn::out_free(d_ptr, s);
+}
+
+void rsn_free_many(void *const *ptrs, size_t count) {
+    for (size_t i = 0; i < count; i++) rsn::pinned().put(ptrs[i]);
+}
+void rsn_dev_free_many(void *const *d_ptrs, size_t count, void *stream) {
+    cudaStream_t s = stream ? (cudaStream_t)stream : rsn::ctx().own_stream;
+    for (size_t i = 0; i < count; i++)
+        if (d_ptrs[i]) rsn::out_free(d_ptrs[i], s);
+}
+
+void rsn_kernel_timing(int enable) {
+    rsn::KTimer &t = rsn::ktimer();
+    t.on.store(false);
+    cudaDeviceSynchronize();
+    {
+        std::lock_guard<std::mutex> g(t.mu);
+        for (auto &r : t.recs) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        t.recs.clear();
+    }
+    t.on.store(enable != 0);
+}
+
+// one line per kernel name: "<name> <launches> <total ms>\n", most expensive first
+size_t rsn_kernel_timing_report(char *buf, size_t cap) {
+    rsn::KTimer &t = rsn::ktimer();
+    cudaDeviceSynchronize();
+    std::vector<std::pair<std::string, std::pair<uint64_t, double>>> rows;
+    {
+        std::lock_guard<std::mutex> g(t.mu);
+        std::unordered_map<std::string, std::pair<uint64_t, double>> agg;
+        for (auto &r : t.recs) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            auto &e = agg[r.name];
+            e.first++;
+            e.second += ms;
+        }
+        rows.assign(agg.begin(), agg.end());
+    }
+    std::sort(rows.begin(), rows.end(), [](const auto &x, const auto &y) { return x.second.second > y.second.second; });
+    std::string out;
+    for (auto &r : rows) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %llu %.6f\n", r.first.c_str(), (unsigned long long)r.second.first, r.second.second);
+        out += line;
+    }
+    if (buf && cap) {
+        const size_t k = std::min(cap - 1, out.size());
+        memcpy(buf, out.data(), k);
+        buf[k] = 0;
+    }
+    return out.size();
 }
 
 uint64_t rsn_kernel_launches(void) { return rsn::g_launches.load(); }

@@ -7,8 +7,8 @@ import numpy as np
 from raisin_b200 import _lib
 
 MAX_FILE = 4 << 20          # kBatchMaxFile
-GROUP_BYTES = 16 << 20
-GROUP_FILES = 512
+GROUP_BYTES = 64 << 20
+GROUP_FILES = 2048
 
 
 def plan(sizes):
@@ -42,9 +42,9 @@ def check(sizes):
     return groups
 
 
-def test_config4_shape_is_eight_groups_of_64():
-    groups = check([262144] * 512)
-    assert sorted(len(v) for v in groups.values()) == [64] * 8
+def test_config4_shape_is_groups_of_256():
+    groups = check([262144] * 4096)
+    assert sorted(len(v) for v in groups.values()) == [256] * 16
 
 
 def test_mixed_sizes_do_not_share_a_group():
