@@ -144,6 +144,8 @@ void arena_free_all() {
 // Everything the calling thread owns on its current device: streams, events, pinned scalars, arena.
 // Runs on rsn_shutdown, when the thread is re-initialised for another device, and when the thread
 // exits (cgo callers migrate over many short-lived OS threads).
+void outs_forget_stream(cudaStream_t s);
+
 static void release_thread_resources() {
     Ctx &c = g_ctx;
     if (!c.ready && !c.own_stream && g_arena.blocks.empty()) return;
@@ -154,11 +156,13 @@ static void release_thread_resources() {
         cudaStreamSynchronize(g_arena.last_stream);
     if (c.own_stream) {
         cudaStreamSynchronize(c.own_stream);
+        outs_forget_stream(c.own_stream);
         cudaStreamDestroy(c.own_stream);
         c.own_stream = nullptr;
     }
     if (c.copy_stream) {
         cudaStreamSynchronize(c.copy_stream);
+        outs_forget_stream(c.copy_stream);
         cudaStreamDestroy(c.copy_stream);
         c.copy_stream = nullptr;
     }
@@ -294,7 +298,7 @@ struct OutCache {
             }
         }
         if (p) {
-            if (last != s) cudaStreamSynchronize(last);  // its previous user may still be reading it
+            if (last && last != s) cudaStreamSynchronize(last);  // its previous user may still be reading it
             return p;
         }
         if (cudaMalloc(&p, c) != cudaSuccess) {
@@ -335,6 +339,16 @@ struct OutCache {
         free_.clear();
         cached = 0;
     }
+    // A stream is about to be destroyed (its owner has synchronised it): cached buffers last used
+    // on it need no further ordering, and must not name it any more.
+    void forget_stream(cudaStream_t s) {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &kv : free_)
+            for (auto &e : kv.second)
+                if (e.second == s) e.second = nullptr;
+        for (auto &kv : live)
+            if (kv.second.last == s) kv.second.last = nullptr;
+    }
 };
 OutCache &outs() {
     static OutCache *c = new OutCache();
@@ -342,6 +356,7 @@ OutCache &outs() {
 }
 }  // namespace
 
+void outs_forget_stream(cudaStream_t s) { outs().forget_stream(s); }
 void *out_alloc(size_t n, cudaStream_t s) { return outs().get(n ? n : 1, s); }
 void out_free(void *p, cudaStream_t s) { outs().put(p, s); }
 

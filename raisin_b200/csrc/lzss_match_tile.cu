@@ -19,6 +19,8 @@
 // L(i) = max_d min(lcp(i-d,i), d, n-i), ties to the larger d (leftmost source, lzss.go:166-184).
 #include "lzss.cuh"
 
+#include <atomic>
+
 namespace rsn {
 
 namespace tile {
@@ -496,28 +498,29 @@ __global__ void kb_match_tile_fix0(const LzFile *__restrict__ files, uint32_t *_
     match_tile_fix0_body(f.enc, (size_t)f.en, f.W, packed + (size_t)blockIdx.y * packed_stride);
 }
 
-int lzss_match_tile(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, cudaStream_t s) {
-    static thread_local bool attr_set = false;
-    const size_t smem = sizeof(tile::Smem);
-    if (!attr_set) {
-        RSN_CUDA(cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    RSN_LAUNCH(k_match_tile, (unsigned)div_up(n, tile::T), tile::THREADS, smem, s, d_enc, n, W, d_packed, (size_t)0);
-    RSN_LAUNCH(k_match_tile_fix0, (unsigned)div_up(min(n, (size_t)W + 2), 128), 128, 0, s, d_enc, n, W, d_packed);
+// cudaFuncSetAttribute is per device: remember which devices have seen it
+static int tile_attr(const void *fn) {
+    static std::atomic<uint64_t> done[2] = {{0}, {0}};  // bit = device; [0] k_match_tile, [1] kb_match_tile
+    const int which = fn == (const void *)k_match_tile ? 0 : 1;
+    int dev = 0;
+    RSN_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done[which].load(std::memory_order_acquire) & bit) return RSN_OK;
+    RSN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tile::Smem)));
+    done[which].fetch_or(bit, std::memory_order_release);
     return RSN_OK;
+}
+
+int lzss_match_tile(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, cudaStream_t s) {
+    return lzss_match_tile_range(d_enc, n, W, d_packed, 0, div_up(n, tile::T), true, s);
 }
 
 // Tiles [tile_lo, tile_hi) only (positions tile*T ...); the caller guarantees that the bytes up to
 // min(n, tile_hi*T + W) are in place.  fix0 must be run once tile 0 and tile 1 are done.
 int lzss_match_tile_range(const uint8_t *d_enc, size_t n, uint32_t W, uint32_t *d_packed, size_t tile_lo,
                           size_t tile_hi, bool run_fix0, cudaStream_t s) {
-    static thread_local bool attr_set = false;
+    RSN_TRY(tile_attr((const void *)k_match_tile));
     const size_t smem = sizeof(tile::Smem);
-    if (!attr_set) {
-        RSN_CUDA(cudaFuncSetAttribute(k_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     if (tile_hi > tile_lo)
         RSN_LAUNCH(k_match_tile, (unsigned)(tile_hi - tile_lo), tile::THREADS, smem, s, d_enc, n, W, d_packed, tile_lo);
     if (run_fix0)
@@ -529,12 +532,8 @@ size_t lzss_match_tile_size() { return tile::T; }
 // every file of a batch: files[f].enc / en / W are device-resident (en <= ecap, W <= window <= 4096)
 int lzss_match_tile_batch(const LzFile *d_files, size_t G, size_t ecap, uint32_t window, uint32_t *d_packed,
                           size_t packed_stride, cudaStream_t s) {
-    static thread_local bool attr_set = false;
+    RSN_TRY(tile_attr((const void *)kb_match_tile));
     const size_t smem = sizeof(tile::Smem);
-    if (!attr_set) {
-        RSN_CUDA(cudaFuncSetAttribute(kb_match_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     const dim3 grid((unsigned)div_up(ecap, tile::T), (unsigned)G);
     RSN_LAUNCH(kb_match_tile, grid, tile::THREADS, smem, s, d_files, d_packed, packed_stride);
     const dim3 gfix((unsigned)div_up((size_t)window + 2, 128), (unsigned)G);

@@ -88,9 +88,9 @@ def test_match_arrays(rsn, oracle):
         torch.cuda.synchronize()
         packed = d_out.cpu().numpy().view(np.uint32)
         np.testing.assert_array_equal(packed >> 16, ln, err_msg=name)
-        # K2 contract: off is exact wherever a reference could be emitted (L >= 4 here; the emit
-        # rule needs L >= 6); for shorter matches only L matters to the parse.
-        sel = ln >= 4
+        # K2 contract: off is exact wherever a reference could be emitted (variant A needs L >= 6,
+        # lzss.go:143; variant B L >= 5, lzss.go:272); for shorter matches only L matters to the parse.
+        sel = ln >= 5
         np.testing.assert_array_equal((packed & 0xFFFF)[sel], off[sel], err_msg=name)
 
 
