@@ -456,7 +456,8 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
         tr.mark(a == ALGO_LZSS ? "lzss stage" : "huffman stage");
     }
     if (device) {  // every file into its own result buffer, one launch for the group
-        std::vector<CopyJob> jobs(G);
+        HostVec<CopyJob> jobs(G);
+        if (!jobs.data()) return RSN_ERR_NOMEM;
         size_t cap = 0;
         int rc = RSN_OK;
         for (size_t f = 0; f < G; f++) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <string.h>
 
 #include "../../include/raisin_b200.h"
 
@@ -90,6 +91,45 @@ struct DevBuf {
     }
     template <typename T>
     T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Pinned host memory from the library's pool.  Every host buffer that a cudaMemcpyAsync touches
+// must be pinned: an "async" copy to or from pageable memory waits inside the driver until the
+// stream has reached it — with the context lock held, so a device-to-host copy queued behind a 4 ms
+// kernel stops every other host thread from launching anything for those 4 ms (that is how the
+// batch path ran its groups' Huffman tree kernels strictly one after another).
+void *host_out_alloc(size_t n);
+template <typename T>
+struct HostVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    HostVec() = default;
+    explicit HostVec(size_t k) { resize(k); }
+    HostVec(const HostVec &) = delete;
+    HostVec &operator=(const HostVec &) = delete;
+    ~HostVec() {
+        if (p) rsn_free(p);
+    }
+    bool resize(size_t k) {  // new elements are zeroed
+        if (k > cap) {
+            T *q = static_cast<T *>(host_out_alloc((k ? k : 1) * sizeof(T)));
+            if (!q) return false;
+            if (p) {
+                memcpy(q, p, n * sizeof(T));
+                rsn_free(p);
+            }
+            p = q;
+            cap = k;
+        }
+        if (k > n) memset(static_cast<void *>(p + n), 0, (k - n) * sizeof(T));
+        n = k;
+        return true;
+    }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
 };
 
 // Stage tracer: with RSN_TRACE=1 in the environment, prints host wall time between marks

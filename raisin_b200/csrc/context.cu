@@ -33,6 +33,7 @@ struct KTimer {
     struct Rec {
         const char *name;
         cudaEvent_t a, b;
+        cudaStream_t s;
     };
     std::vector<Rec> recs;
 };
@@ -45,7 +46,7 @@ KTimer &ktimer() {
 int ktime_begin(const char *name, cudaStream_t s) {
     KTimer &t = ktimer();
     if (!t.on.load(std::memory_order_relaxed)) return -1;
-    KTimer::Rec r{name, nullptr, nullptr};
+    KTimer::Rec r{name, nullptr, nullptr, s};
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
         cudaGetLastError();
         return -1;
@@ -642,6 +643,21 @@ void rsn_kernel_timing(int enable) {
 size_t rsn_kernel_timing_report(char *buf, size_t cap) {
     rsn::KTimer &t = rsn::ktimer();
     cudaDeviceSynchronize();
+    if (const char *path = getenv("RSN_KTIME_TIMELINE")) {  // every launch: name, stream, start and end (ms since the first)
+        std::lock_guard<std::mutex> g(t.mu);
+        if (FILE *f = fopen(path, "w")) {
+            for (auto &r : t.recs) {
+                float a = 0.f, b = 0.f;
+                if (cudaEventElapsedTime(&a, t.recs[0].a, r.a) != cudaSuccess ||
+                    cudaEventElapsedTime(&b, t.recs[0].a, r.b) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                fprintf(f, "%s %p %.4f %.4f\n", r.name, (void *)r.s, a, b);
+            }
+            fclose(f);
+        }
+    }
     std::vector<std::pair<std::string, std::pair<uint64_t, double>>> rows;
     {
         std::lock_guard<std::mutex> g(t.mu);

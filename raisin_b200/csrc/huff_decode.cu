@@ -526,8 +526,9 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
     });
     tr.mark("host headers");
     // leaves of all files in one upload; trees and 12-bit tables on the device (huff_tree.cu)
-    std::vector<HdecFile> h(G);
-    static thread_local std::vector<uint8_t> tab;  // keeps its pages between groups
+    HostVec<HdecFile> h(G);
+    if (!h.data()) return RSN_ERR_NOMEM;
+    static thread_local HostVec<uint8_t> tab;  // pinned staging: kept between groups
     std::vector<size_t> o_freq(G, 0), o_rune(G, 0), o_nodes(G, 0), o_parent(G, 0), o_lut(G, 0);
     size_t tab_n = 0, scr_n = 0;
     auto room = [](size_t &cursor, size_t bytes) {
@@ -553,7 +554,7 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         subs_total += h[f].subs;
         subs_cap = std::max<size_t>(subs_cap, h[f].subs);
     }
-    if (tab.size() < tab_n) tab.resize(tab_n);
+    if (tab.size() < tab_n + 256 && !tab.resize(tab_n + 256)) return RSN_ERR_NOMEM;
     uint8_t *const tabp = tab.data();
     for (size_t f = 0; f < G; f++) {
         if (!h[f].subs) continue;
@@ -571,7 +572,8 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
     RSN_TRY(cnt.alloc(subs_total * 8 + 8, s));
     RSN_TRY(off.alloc(subs_total * 8 + 8, s));
     RSN_TRY(flag.alloc(16, s));
-    std::vector<TreeJob> jobs(G);
+    HostVec<TreeJob> jobs(G);
+    if (!jobs.data()) return RSN_ERR_NOMEM;
     for (size_t f = 0; f < G; f++) {
         jobs[f] = TreeJob{};
         if (!h[f].subs) continue;

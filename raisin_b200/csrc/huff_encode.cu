@@ -522,33 +522,33 @@ struct HencHost {
 };
 
 // runes are below 2^21: three byte-wise counting passes
-void sort_runes(std::vector<uint32_t> &v) {
-    if (v.size() < 256) {
-        std::sort(v.begin(), v.end());
+void sort_runes(uint32_t *v, size_t n) {
+    if (n < 256) {
+        std::sort(v, v + n);
         return;
     }
-    std::vector<uint32_t> tmp(v.size());
-    uint32_t *src = v.data(), *dst = tmp.data();
+    std::vector<uint32_t> tmp(n);
+    uint32_t *src = v, *dst = tmp.data();
     for (int byte = 0; byte < 3; byte++) {
         size_t cnt[257] = {0};
-        for (size_t i = 0; i < v.size(); i++) cnt[((src[i] >> (8 * byte)) & 0xFF) + 1]++;
+        for (size_t i = 0; i < n; i++) cnt[((src[i] >> (8 * byte)) & 0xFF) + 1]++;
         for (int d = 0; d < 256; d++) cnt[d + 1] += cnt[d];
-        for (size_t i = 0; i < v.size(); i++) dst[cnt[(src[i] >> (8 * byte)) & 0xFF]++] = src[i];
+        for (size_t i = 0; i < n; i++) dst[cnt[(src[i] >> (8 * byte)) & 0xFF]++] = src[i];
         std::swap(src, dst);
     }
-    if (src != v.data()) std::copy(src, src + v.size(), v.data());
+    if (src != v) std::copy(src, src + n, v);
 }
 
 // histogram -> leaves in the reference's order, header bytes (huffman.go:312-318)
-void henc_host_plan(const uint32_t *hist, std::vector<uint32_t> &big, HencHost &pl) {
+void henc_host_plan(const uint32_t *hist, uint32_t *big, size_t big_n, HencHost &pl) {
     std::vector<HuffLeaf> leaves;
     for (int r = 0; r < kSmallBins; r++)
         if (hist[r]) leaves.push_back(HuffLeaf{(int64_t)hist[r], r});
-    sort_runes(big);
+    sort_runes(big, big_n);
     size_t nbig = 0;
-    for (size_t i = 0; i < big.size();) {
+    for (size_t i = 0; i < big_n;) {
         size_t j = i;
-        while (j < big.size() && big[j] == big[i]) j++;
+        while (j < big_n && big[j] == big[i]) j++;
         leaves.push_back(HuffLeaf{(int64_t)(j - i), (int32_t)big[i]});
         nbig++;
         i = j;
@@ -597,7 +597,8 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     HencBatch b{};
     b.big_stride = cap / 2 + 16;
     b.tc_stride = tiles_cap + 1;
-    std::vector<HencFile> h(G);
+    HostVec<HencFile> h(G);
+    if (!h.data()) return RSN_ERR_NOMEM;
     for (size_t f = 0; f < G; f++) {
         h[f] = HencFile{};
         h[f].in = in.ptr[f];
@@ -619,16 +620,20 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     RSN_CUDA(cudaMemcpyAsync(files.p, h.data(), G * sizeof(HencFile), cudaMemcpyHostToDevice, s));
     RSN_CUDA(cudaMemsetAsync(hist.p, 0, G * kHistStride * 4, s));
     RSN_LAUNCH(kb_rune_hist, dim3((unsigned)div_up(tiles_cap, kHistTilesPerCta), g), kTileThreads, 0, s, b);
-    std::vector<uint32_t> h_hist(G * kHistStride);
+    HostVec<uint32_t> h_hist(G * kHistStride);
+    if (!h_hist.data()) return RSN_ERR_NOMEM;
     RSN_CUDA(cudaMemcpyAsync(h_hist.data(), hist.p, G * kHistStride * 4, cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HencFile), cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaStreamSynchronize(s));
     tr.mark("hist");
-    std::vector<std::vector<uint32_t>> h_big(G);
+    // the per-file lists of runes >= 256, back to back in one pinned buffer
+    std::vector<size_t> big_at(G + 1, 0);
+    for (size_t f = 0; f < G; f++) big_at[f + 1] = big_at[f] + h[f].big_n;
+    HostVec<uint32_t> h_big(big_at[G] + 1);
+    if (!h_big.data()) return RSN_ERR_NOMEM;
     for (size_t f = 0; f < G; f++) {
         if (!h[f].big_n) continue;
-        h_big[f].resize(h[f].big_n);
-        RSN_CUDA(cudaMemcpyAsync(h_big[f].data(), b.big + f * b.big_stride, (size_t)h[f].big_n * 4,
+        RSN_CUDA(cudaMemcpyAsync(h_big.data() + big_at[f], b.big + f * b.big_stride, (size_t)h[f].big_n * 4,
                                  cudaMemcpyDeviceToHost, s));
     }
     RSN_CUDA(cudaStreamSynchronize(s));
@@ -641,10 +646,10 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
             plan[f].rc = out.rc[f];
             return;
         }
-        henc_host_plan(h_hist.data() + f * kHistStride, h_big[f], plan[f]);
+        henc_host_plan(h_hist.data() + f * kHistStride, h_big.data() + big_at[f], big_at[f + 1] - big_at[f], plan[f]);
     });
     tr.mark("host leaves+headers");
-    static thread_local std::vector<uint8_t> tab;  // staging: keeps its pages between groups
+    static thread_local HostVec<uint8_t> tab;  // pinned staging: kept between groups
     std::vector<size_t> o_freq(G), o_rune(G), o_pre(G), o_small(G), o_btab(G), o_nodes(G), o_parent(G);
     size_t tab_n = 0, zero_n = 0, ff_n = 0, scr_n = 0;
     auto room = [](size_t &cursor, size_t bytes) {
@@ -666,7 +671,7 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
         o_nodes[f] = room(scr_n, (2 * k) * sizeof(HuffNodeDev));
         o_parent[f] = room(scr_n, (2 * k) * 4);
     }
-    if (tab.size() < tab_n) tab.resize(tab_n);
+    if (tab.size() < tab_n + 256 && !tab.resize(tab_n + 256)) return RSN_ERR_NOMEM;
     uint8_t *const tabp = tab.data();  // (a thread_local name inside the lambda would be the helper thread's own)
     parallel_for(G, batch_host_threads(), [&, tabp](size_t f) {
         if (plan[f].rc != RSN_OK || plan[f].per_file) return;
@@ -680,7 +685,8 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     RSN_TRY(dff.alloc(ff_n + 256, s));
     RSN_TRY(dscr.alloc(scr_n + 256, s));
     RSN_TRY(djobs.alloc(G * sizeof(TreeJob), s));
-    std::vector<TreeJob> jobs(G);
+    HostVec<TreeJob> jobs(G);
+    if (!jobs.data()) return RSN_ERR_NOMEM;
     for (size_t f = 0; f < G; f++) {
         TreeJob &j = jobs[f];
         j = TreeJob{};

@@ -22,18 +22,34 @@ __device__ __forceinline__ bool heap_less(uint64_t a, uint64_t b) { return (uint
 
 // container/heap.down / up (Go 1.15) with the moving element carried in a register: the array ends
 // up exactly as after Go's swaps.
+// Two levels per round trip to shared memory: the four grandchildren are loaded together with the two
+// children, so the second comparison does not wait for another load (the replay is a chain of
+// dependent loads, and one lane per file runs it).
 __device__ __forceinline__ void heap_down(uint64_t *h, int i, int n) {
     const uint64_t v = h[i];
     for (;;) {
         const int j1 = 2 * i + 1;
         if (j1 >= n) break;
         const int j2 = j1 + 1 < n ? j1 + 1 : j1;
+        const int g = 2 * j1 + 1;  // grandchildren g .. g+3 (children of j1, then of j1+1)
         const uint64_t a = h[j1], b = h[j2];
+        const uint64_t g0 = g < n ? h[g] : 0, g1 = g + 1 < n ? h[g + 1] : 0, g2 = g + 2 < n ? h[g + 2] : 0,
+                       g3 = g + 3 < n ? h[g + 3] : 0;
         const bool right = heap_less(b, a);  // j2 == j1 gives false
         const uint64_t c = right ? b : a;
         if (!heap_less(c, v)) break;
         h[i] = c;
         i = right ? j2 : j1;
+        // second level from the prefetched values
+        const int k1 = 2 * i + 1;
+        if (k1 >= n) break;
+        const bool has2 = k1 + 1 < n;
+        const uint64_t a2 = right ? g2 : g0, b2 = has2 ? (right ? g3 : g1) : a2;
+        const bool right2 = heap_less(b2, a2);
+        const uint64_t c2 = right2 ? b2 : a2;
+        if (!heap_less(c2, v)) break;
+        h[i] = c2;
+        i = right2 ? k1 + 1 : k1;
     }
     h[i] = v;
 }

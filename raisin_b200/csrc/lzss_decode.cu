@@ -777,7 +777,8 @@ int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     const size_t tiles_cap = div_up(cap, kTile);
     DecBatch b{};
     b.tc_stride = tiles_cap + 1;
-    std::vector<DecFile> h(G);
+    HostVec<DecFile> h(G);
+    if (!h.data()) return RSN_ERR_NOMEM;
     for (size_t f = 0; f < G; f++) {
         h[f] = DecFile{};
         h[f].in = in.ptr[f];
@@ -824,9 +825,51 @@ int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
         total += (h[f].sbn + 16 + 255) & ~(uint64_t)255;
         sb_cap = std::max<size_t>(sb_cap, h[f].sbn);
     }
-    // distances and work lists take 12 bytes per decoded byte: groups that decode to more than
-    // 256 MiB go file by file
-    if (total > ((size_t)256 << 20)) return RSN_ERR_UNSUPPORTED;
+    // distances and work lists take 12 bytes per decoded byte: a group that decodes to more than
+    // 256 MiB is cut in two (compressed sizes say little about decoded ones: 1365 log files of config 4
+    // are 50 MB compressed and 341 MiB decoded); a single file that large goes through the per-file call
+    if (total > ((size_t)256 << 20)) {
+        if (G == 1) return RSN_ERR_UNSUPPORTED;
+        const size_t half = G / 2;
+        for (int part = 0; part < 2; part++) {
+            const size_t lo = part ? half : 0, hi = part ? G : half;
+            BatchIO sub_in, sub_out;
+            sub_in.resize(hi - lo);
+            for (size_t f = lo; f < hi; f++) {
+                sub_in.ptr[f - lo] = in.ptr[f];
+                sub_in.n[f - lo] = in.n[f];
+                sub_in.rc[f - lo] = out.rc[f];
+            }
+            int rc = lzss_decompress_batch(sub_in, sub_out, s);
+            if (rc == RSN_ERR_UNSUPPORTED) {  // one huge file left: per-file call
+                sub_out.resize(hi - lo);
+                sub_out.rc = sub_in.rc;
+                for (size_t f = 0; f < hi - lo; f++) {
+                    if (sub_in.rc[f] != RSN_OK) continue;
+                    uint8_t *r = nullptr;
+                    size_t rn = 0;
+                    sub_out.rc[f] = lzss_decompress_dev(sub_in.ptr[f], (size_t)sub_in.n[f], &r, &rn, s);
+                    if (sub_out.rc[f] != RSN_OK) continue;
+                    sub_out.ptr[f] = r;
+                    sub_out.n[f] = rn;
+                    sub_out.owned.push_back(r);
+                }
+                rc = RSN_OK;
+            }
+            if (rc != RSN_OK) {
+                sub_out.release(s);
+                out.release(s);
+                return rc;
+            }
+            for (size_t f = lo; f < hi; f++) {
+                out.ptr[f] = sub_out.ptr[f - lo];
+                out.n[f] = sub_out.n[f - lo];
+                out.rc[f] = sub_out.rc[f - lo];
+            }
+            out.owned.insert(out.owned.end(), sub_out.owned.begin(), sub_out.owned.end());
+        }
+        return RSN_OK;
+    }
     // ---- phase B: literals and distances, then the chase
     DevBuf sb, dist, wl[2], cnt;
     RSN_TRY(sb.alloc_out(total + 256, s));

@@ -866,7 +866,8 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     b.vis_stride = blocks_cap * (kPB / 16);
     b.bb_stride = blocks_cap + 1;
 
-    std::vector<LzFile> h_files(G);
+    HostVec<LzFile> h_files(G);
+    if (!h_files.data()) return RSN_ERR_NOMEM;
     for (size_t f = 0; f < G; f++) {
         LzFile r{};
         r.in = in.ptr[f];
@@ -915,12 +916,14 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     if (b.top) RSN_LAUNCH(kb_parse_down, dim3((unsigned)div_up(regions1, 128), g), 128, 0, s, b);
     RSN_LAUNCH(kb_emit_plan, dim3((unsigned)blocks_cap, g), kPT, 0, s, b);
     RSN_LAUNCH(kb_emit_finish, g, 256, 0, s, b);
-    std::vector<uint64_t> h_outn(G);
+    HostVec<uint64_t> h_outn(G);
+    if (!h_outn.data()) return RSN_ERR_NOMEM;
     RSN_CUDA(cudaMemcpyAsync(h_outn.data(), outn.p, G * 8, cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaStreamSynchronize(s));
 
     // one result buffer for the group, files at 256-byte aligned offsets
-    std::vector<uint8_t *> h_outp(G);
+    HostVec<uint8_t *> h_outp(G);
+    if (!h_outp.data()) return RSN_ERR_NOMEM;
     size_t total = 0;
     for (size_t f = 0; f < G; f++) total += round_up(h_outn[f] + 16, 256);
     DevBuf res;
