@@ -73,6 +73,17 @@ void rsn_host_free(void *p);
  * `in` is only read during the call.  `*out` is library-owned; release with rsn_free().
  */
 int rsn_lzss_compress(const uint8_t *in, size_t n, int64_t window, int variant, uint8_t **out, size_t *out_n);
+/*
+ * lz.CompressAsync of ONE large stream with the match search sharded by position range over
+ * `ngpus` shards (BASELINE configs[4]); same bytes as rsn_lzss_compress.  One host thread and CUDA
+ * stream per shard inside the call; shard g runs on device g mod the device count.  Each shard holds
+ * only its range plus a window of bytes either side; what crosses between GPUs is those halos (peer
+ * copies) and, through the host, an 8 KB table per shard.  RSN_LZSS_ITER runs on one GPU.
+ */
+int rsn_lzss_compress_sharded(const uint8_t *in, size_t n, int64_t window, int variant, int ngpus, uint8_t **out,
+                              size_t *out_n);
+/* Bytes copied GPU-to-GPU by the calling thread's last rsn_lzss_compress_sharded. */
+uint64_t rsn_sharded_peer_bytes(void);
 /* Replaces lz.Decompress (lzss.go:323-364). */
 int rsn_lzss_decompress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
 /* Replaces huffman.Compress (huffman.go:299-325). */

@@ -14,7 +14,7 @@ SO_PATH = os.path.join(_HERE, "libraisin_b200.so")
 # every symbol include/raisin_b200.h declares
 EXPORTS = [
     "rsn_init", "rsn_shutdown", "rsn_strerror", "rsn_last_cuda_error", "rsn_free", "rsn_free_many", "rsn_dev_free_many", "rsn_host_alloc",
-    "rsn_host_free", "rsn_lzss_compress", "rsn_lzss_decompress", "rsn_huff_compress", "rsn_huff_decompress",
+    "rsn_host_free", "rsn_lzss_compress", "rsn_lzss_compress_sharded", "rsn_sharded_peer_bytes", "rsn_lzss_decompress", "rsn_huff_compress", "rsn_huff_decompress",
     "rsn_compress_layers", "rsn_decompress_layers", "rsn_batch_layers", "rsn_batch_plan", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
     "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_free", "rsn_dev_download", "rsn_dev_upload",
     "rsn_dev_lzss_match", "rsn_dev_lzss_emit", "rsn_dev_lzss_escape",
@@ -67,6 +67,10 @@ def lib():
     L.rsn_host_free.argtypes = [C.c_void_p]
     L.rsn_host_free.restype = None
     L.rsn_lzss_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_int64, C.c_int, u8pp, szp]
+    L.rsn_lzss_compress_sharded.argtypes = [C.c_void_p, C.c_size_t, C.c_int64, C.c_int, C.c_int, u8pp, szp]
+    L.rsn_lzss_compress_sharded.restype = C.c_int
+    L.rsn_sharded_peer_bytes.argtypes = []
+    L.rsn_sharded_peer_bytes.restype = C.c_uint64
     L.rsn_lzss_decompress.argtypes = [C.c_void_p, C.c_size_t, u8pp, szp]
     L.rsn_huff_compress.argtypes = [C.c_void_p, C.c_size_t, u8pp, szp]
     L.rsn_huff_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, u8pp, szp]

@@ -152,6 +152,19 @@ int rsn_lzss_compress(const uint8_t *in, size_t n, int64_t window, int variant, 
     return to_host(r, rn, out, out_n, s);
 }
 
+// BASELINE configs[4]: lz.CompressAsync of one large stream with the match search sharded by
+// position range over `ngpus` shards (shard g on device g mod the device count).  The iterative
+// variant has no sharded form (its start-of-match test scans the whole history): it runs on one GPU.
+int rsn_lzss_compress_sharded(const uint8_t *in, size_t n, int64_t window, int variant, int ngpus, uint8_t **out,
+                              size_t *out_n) {
+    if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
+    if (variant != RSN_LZSS_ASYNC && variant != RSN_LZSS_ITER) return RSN_ERR_INVALID_ARG;
+    if (variant == RSN_LZSS_ITER || ngpus <= 1) return rsn_lzss_compress(in, n, window, variant, out, out_n);
+    RSN_TRY(ensure_ctx());
+    return lzss_compress_sharded(in, n, window, ngpus, out, out_n);
+}
+uint64_t rsn_sharded_peer_bytes(void) { return lzss_sharded_last_peer_bytes(); }
+
 int rsn_lzss_decompress(const uint8_t *in, size_t n, uint8_t **out, size_t *out_n) {
     if ((!in && n) || !out || !out_n) return RSN_ERR_INVALID_ARG;
     RSN_TRY(ensure_ctx());

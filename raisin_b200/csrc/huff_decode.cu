@@ -219,7 +219,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
     ArenaScope scope(s);
     Trace tr("hd", s);
     // ---- host: find the first 5C 0A (strings.SplitN, huffman.go:261) and parse the header
-    std::vector<uint8_t> h_copy;
+    HostVec<uint8_t> h_copy;  // pinned (see HostVec)
     const uint8_t *h = h_in;
     size_t hn = n;
     auto find_sep = [](const uint8_t *b, size_t len) -> ptrdiff_t {
@@ -235,7 +235,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
         size_t take = n < ((size_t)64 << 10) ? n : ((size_t)64 << 10);
         size_t have = 0;
         for (;;) {
-            h_copy.resize(take);
+            if (!h_copy.resize(take)) return RSN_ERR_NOMEM;
             RSN_CUDA(cudaMemcpyAsync(h_copy.data() + have, d_in + have, take - have, cudaMemcpyDeviceToHost, s));
             RSN_CUDA(cudaStreamSynchronize(s));
             // the separator may straddle the previous chunk boundary: rescan from one byte before it
@@ -299,10 +299,14 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
 
     DevBuf nodes;
     RSN_TRY(nodes.alloc(tree.nodes.size() * sizeof(HuffNode), s));
-    RSN_CUDA(cudaMemcpyAsync(nodes.p, tree.nodes.data(), tree.nodes.size() * sizeof(HuffNode), cudaMemcpyHostToDevice, s));
+    HostVec<HuffNode> h_nodes(tree.nodes.size());  // pinned (see HostVec)
+    if (!h_nodes.data()) return RSN_ERR_NOMEM;
+    memcpy(h_nodes.data(), tree.nodes.data(), tree.nodes.size() * sizeof(HuffNode));
+    RSN_CUDA(cudaMemcpyAsync(nodes.p, h_nodes.data(), tree.nodes.size() * sizeof(HuffNode), cudaMemcpyHostToDevice, s));
 
     // lookup table over the first kLutBits bits of a code
-    std::vector<uint32_t> h_lut((size_t)1 << kLutBits);
+    HostVec<uint32_t> h_lut((size_t)1 << kLutBits);
+    if (!h_lut.data()) return RSN_ERR_NOMEM;
     for (uint32_t idx = 0; idx < h_lut.size(); idx++) {
         int32_t node = tree.root;
         uint32_t len = 0;

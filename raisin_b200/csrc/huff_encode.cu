@@ -336,7 +336,8 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
                list.as<RuneFreq>(), count.as<unsigned long long>());
     uint64_t k = 0;
     RSN_TRY(read_u64(count.as<uint64_t>(), &k, s));
-    std::vector<RuneFreq> h_list(k);
+    HostVec<RuneFreq> h_list(k);  // pinned (see HostVec)
+    if (!h_list.data()) return RSN_ERR_NOMEM;
     RSN_CUDA(cudaMemcpyAsync(h_list.data(), list.p, k * sizeof(RuneFreq), cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaStreamSynchronize(s));
     list.reset();
@@ -351,7 +352,8 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     if (!huff_codes(tree, codes)) return RSN_ERR_UNSUPPORTED;  // a code longer than 64 bits
     std::vector<uint8_t> hdr;
     huff_header(leaves, hdr);
-    std::vector<CodeEntry> h_codes(codes.size());
+    HostVec<CodeEntry> h_codes(codes.size());
+    if (!h_codes.data()) return RSN_ERR_NOMEM;
     uint64_t total_bits = 0;
     uint32_t maxlen = 0;
     for (size_t i = 0; i < codes.size(); i++) {
@@ -378,10 +380,12 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     DevBuf out;
     RSN_TRY(out.alloc_out(total + 16, s));
     RSN_CUDA(cudaMemsetAsync(out.p, 0, total + 16, s));
-    std::vector<uint8_t> pre(hdr);
-    pre.push_back(0x5C);
-    pre.push_back(0x0A);
-    pre.push_back((uint8_t)pad);
+    HostVec<uint8_t> pre(hdr.size() + 3);
+    if (!pre.data()) return RSN_ERR_NOMEM;
+    memcpy(pre.data(), hdr.data(), hdr.size());
+    pre[hdr.size()] = 0x5C;
+    pre[hdr.size() + 1] = 0x0A;
+    pre[hdr.size() + 2] = (uint8_t)pad;
     RSN_CUDA(cudaMemcpyAsync(out.p, pre.data(), pre.size(), cudaMemcpyHostToDevice, s));
     if (total_bits) {
         DevBuf tb, tbo;

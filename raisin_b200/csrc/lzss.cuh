@@ -38,6 +38,8 @@ int lzss_compress_dev_ex(const uint8_t *d_in, size_t n, int64_t window, int vari
                          uint8_t **d_out, size_t *out_n, cudaStream_t s);
 int lzss_emit_dev(const uint8_t *d_enc, size_t n, int64_t window, int variant, const uint32_t *d_packed,
                   uint8_t **d_out, size_t *out_n, cudaStream_t s);
+int lzss_compress_sharded(const uint8_t *in, size_t n, int64_t window, int shards, uint8_t **out, size_t *out_n);
+uint64_t lzss_sharded_last_peer_bytes();
 int lzss_escape_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s);
 int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_n, cudaStream_t s);
 

@@ -12,6 +12,11 @@
 #include "lzss.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 namespace rsn {
 
@@ -246,11 +251,13 @@ struct ParseLevels {
 
 // one orbit step at level `lvl` from absolute position p (p < n, p inside region p / rsize)
 __device__ __forceinline__ size_t level_step(size_t p, int lvl, size_t rsize, const uint16_t *__restrict__ E0,
-                                             const uint16_t *__restrict__ T, uint32_t J) {
+                                             const uint16_t *__restrict__ T, uint32_t J, size_t n) {
     const size_t r = p / rsize;
     const size_t end = (r + 1) * rsize;
     if (lvl == 0) return end + __ldg(E0 + p);
-    return end + __ldg(T + r * (size_t)(J + 1) + (p - r * rsize));
+    // a region cut short by the end of the array exits relative to that end (the array may be one
+    // shard of a longer stream, whose parse goes on in the next shard)
+    return min(end, n) + __ldg(T + r * (size_t)(J + 1) + (p - r * rsize));
 }
 
 // T_l[r][rel] for rel in [0, J]: follow level l-1 until leaving region r (or the input).
@@ -259,10 +266,10 @@ __device__ __forceinline__ void parse_up_body(const uint16_t *__restrict__ E0, c
                                               size_t rsize_cur, uint32_t J, size_t n, size_t r) {
     const uint32_t rel = blockIdx.x * blockDim.x + threadIdx.x;
     if (rel > J) return;
-    const size_t start = r * rsize_cur, end = start + rsize_cur;
+    const size_t start = r * rsize_cur, end = min(start + rsize_cur, n);
     size_t p = start + rel;
-    while (p < end && p < n) p = level_step(p, lvl - 1, rsize_prev, E0, Tprev, J);
-    Tcur[r * (size_t)(J + 1) + rel] = (uint16_t)(p >= end ? p - end : 0);
+    while (p < end) p = level_step(p, lvl - 1, rsize_prev, E0, Tprev, J, n);
+    Tcur[r * (size_t)(J + 1) + rel] = (uint16_t)(p - end);
 }
 __global__ void k_parse_up(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tprev,
                            uint16_t *__restrict__ Tcur, int lvl, size_t rsize_prev, size_t rsize_cur, uint32_t J,
@@ -273,18 +280,29 @@ __global__ void k_parse_up(const uint16_t *__restrict__ E0, const uint16_t *__re
 // sequential walk over the (<= kFan) top-level regions
 __device__ __forceinline__ void parse_top_body(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Ttop,
                                                int lvl, size_t rsize, size_t regions, uint32_t J, size_t n,
-                                               uint64_t *__restrict__ entry) {
-    size_t p = 0;
+                                               uint64_t *__restrict__ entry, size_t first = 0) {
+    size_t p = first;  // where the orbit enters the array (0 for a whole stream)
     for (size_t r = 0; r < regions; r++) {
         entry[r] = p;
         const size_t end = (r + 1) * rsize;
-        if (p < end && p < n) p = level_step(p, lvl, rsize, E0, Ttop, J);
+        if (p < end && p < n) p = level_step(p, lvl, rsize, E0, Ttop, J, n);
     }
 }
 __global__ void k_parse_top(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Ttop, int lvl,
-                            size_t rsize, size_t regions, uint32_t J, size_t n, uint64_t *__restrict__ entry) {
+                            size_t rsize, size_t regions, uint32_t J, size_t n, uint64_t *__restrict__ entry,
+                            size_t first) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    parse_top_body(E0, Ttop, lvl, rsize, regions, J, n, entry);
+    parse_top_body(E0, Ttop, lvl, rsize, regions, J, n, entry, first);
+}
+// One shard of a longer stream: where the orbit leaves the array (relative to its end) for every
+// possible entry offset 0..J.  Composed over the shards on the host, this gives every shard's true entry.
+__global__ void k_shard_exits(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Ttop, int lvl,
+                              size_t rsize, uint32_t J, size_t n, uint16_t *__restrict__ exits) {
+    const uint32_t rel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rel > J) return;
+    size_t p = rel;
+    while (p < n) p = level_step(p, lvl, rsize, E0, Ttop, J, n);
+    exits[rel] = (uint16_t)(p - n);
 }
 
 // entries of the children (level lvl-1) of each level-lvl region
@@ -301,7 +319,7 @@ __device__ __forceinline__ void parse_down_body(const uint16_t *__restrict__ E0,
         if (cr >= regions_child) break;
         entry_child[cr] = p;
         const size_t end = (cr + 1) * rsize_child;
-        if (p < end && p < n) p = level_step(p, child_lvl, rsize_child, E0, Tchild, J);
+        if (p < end && p < n) p = level_step(p, child_lvl, rsize_child, E0, Tchild, J, n);
     }
 }
 __global__ void k_parse_down(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tchild, int child_lvl,
@@ -553,50 +571,77 @@ __global__ void __launch_bounds__(256) k_start_bits(const uint8_t *__restrict__ 
 
 // ============================================================================= host orchestration
 
-static int parse_and_emit(const uint8_t *d_enc, size_t n, ParseCfg cfg, const uint32_t *d_lo, uint8_t **d_out,
-                          size_t *out_n, cudaStream_t s) {
-    const size_t blocks = div_up(n, kPB);
-    const uint32_t J = cfg.J;
+// The parse of one array of match records, in three steps so that a shard of a longer stream can put
+// an exchange between them: tables (no entry needed), resolution from the position where the orbit
+// enters the array, emit.
+struct ParsePlan {
     ParseLevels lv;
+    size_t blocks = 0;
+    DevBuf E0, T[8], entry[8], vis, bb, bo;
+};
+
+static int parse_build_tables(const ParseCfg &cfg, const uint32_t *d_lo, size_t n, ParsePlan &pp, cudaStream_t s) {
+    pp.blocks = div_up(n, kPB);
+    const uint32_t J = cfg.J;
+    ParseLevels &lv = pp.lv;
     lv.top = 0;
     lv.rsize[0] = kPB;
-    lv.regions[0] = blocks;
+    lv.regions[0] = pp.blocks;
     while (lv.regions[lv.top] > (size_t)kFan) {
         lv.rsize[lv.top + 1] = lv.rsize[lv.top] * kFan;
         lv.regions[lv.top + 1] = div_up(n, lv.rsize[lv.top + 1]);
         lv.top++;
     }
-    DevBuf E0, T[8], entry[8];
-    RSN_TRY(E0.alloc(blocks * kPB * 2 + 64, s));
-    RSN_LAUNCH(k_parse_exits, (unsigned)blocks, kPT, 0, s, cfg, d_lo, n, E0.as<uint16_t>());
+    RSN_TRY(pp.E0.alloc(pp.blocks * kPB * 2 + 64, s));
+    RSN_LAUNCH(k_parse_exits, (unsigned)pp.blocks, kPT, 0, s, cfg, d_lo, n, pp.E0.as<uint16_t>());
     for (int l = 1; l <= lv.top; l++) {
-        RSN_TRY(T[l].alloc(lv.regions[l] * (size_t)(J + 1) * 2, s));
+        RSN_TRY(pp.T[l].alloc(lv.regions[l] * (size_t)(J + 1) * 2, s));
         dim3 grid((unsigned)div_up((size_t)J + 1, 256), (unsigned)lv.regions[l]);
-        RSN_LAUNCH(k_parse_up, grid, 256, 0, s, E0.as<uint16_t>(), T[l - 1].as<uint16_t>(), T[l].as<uint16_t>(), l,
+        RSN_LAUNCH(k_parse_up, grid, 256, 0, s, pp.E0.as<uint16_t>(), pp.T[l - 1].as<uint16_t>(), pp.T[l].as<uint16_t>(), l,
                    lv.rsize[l - 1], lv.rsize[l], J, n);
     }
-    for (int l = 0; l <= lv.top; l++) RSN_TRY(entry[l].alloc(lv.regions[l] * 8, s));
-    RSN_LAUNCH(k_parse_top, 1, 32, 0, s, E0.as<uint16_t>(), T[lv.top].as<uint16_t>(), lv.top, lv.rsize[lv.top],
-               lv.regions[lv.top], J, n, entry[lv.top].as<uint64_t>());
+    return RSN_OK;
+}
+
+// entries of every block for an orbit that enters the array at `first`, orbit bitmap, output size
+static int parse_resolve(const ParseCfg &cfg, const uint32_t *d_lo, size_t n, size_t first, ParsePlan &pp,
+                         uint64_t *total, cudaStream_t s) {
+    const uint32_t J = cfg.J;
+    const ParseLevels &lv = pp.lv;
+    const size_t blocks = pp.blocks;
+    for (int l = 0; l <= lv.top; l++) RSN_TRY(pp.entry[l].alloc(lv.regions[l] * 8, s));
+    RSN_LAUNCH(k_parse_top, 1, 32, 0, s, pp.E0.as<uint16_t>(), pp.T[lv.top].as<uint16_t>(), lv.top, lv.rsize[lv.top],
+               lv.regions[lv.top], J, n, pp.entry[lv.top].as<uint64_t>(), first);
     for (int l = lv.top; l >= 1; l--) {
-        RSN_LAUNCH(k_parse_down, (unsigned)div_up(lv.regions[l], 128), 128, 0, s, E0.as<uint16_t>(),
-                   T[l - 1].as<uint16_t>(), l - 1, lv.rsize[l - 1], lv.regions[l], lv.regions[l - 1], J, n,
-                   entry[l].as<uint64_t>(), entry[l - 1].as<uint64_t>());
+        RSN_LAUNCH(k_parse_down, (unsigned)div_up(lv.regions[l], 128), 128, 0, s, pp.E0.as<uint16_t>(),
+                   pp.T[l - 1].as<uint16_t>(), l - 1, lv.rsize[l - 1], lv.regions[l], lv.regions[l - 1], J, n,
+                   pp.entry[l].as<uint64_t>(), pp.entry[l - 1].as<uint64_t>());
     }
-    DevBuf vis, bb, bo;
-    RSN_TRY(vis.alloc(blocks * (kPB / 16) * 2 + 16, s));
-    RSN_TRY(bb.alloc(blocks * 8, s));
-    RSN_TRY(bo.alloc((blocks + 1) * 8, s));
-    RSN_LAUNCH(k_emit_plan, (unsigned)blocks, kPT, 0, s, cfg, d_lo, n, entry[0].as<uint64_t>(), vis.as<uint16_t>(),
-               bb.as<uint64_t>());
-    E0.reset();
-    RSN_TRY(spine_scan_u64(bb.as<uint64_t>(), bo.as<uint64_t>(), bo.as<uint64_t>() + blocks, blocks, s));
+    RSN_TRY(pp.vis.alloc(blocks * (kPB / 16) * 2 + 16, s));
+    RSN_TRY(pp.bb.alloc(blocks * 8, s));
+    RSN_TRY(pp.bo.alloc((blocks + 1) * 8, s));
+    RSN_LAUNCH(k_emit_plan, (unsigned)blocks, kPT, 0, s, cfg, d_lo, n, pp.entry[0].as<uint64_t>(), pp.vis.as<uint16_t>(),
+               pp.bb.as<uint64_t>());
+    RSN_TRY(spine_scan_u64(pp.bb.as<uint64_t>(), pp.bo.as<uint64_t>(), pp.bo.as<uint64_t>() + blocks, blocks, s));
+    return read_u64(pp.bo.as<uint64_t>() + blocks, total, s);
+}
+
+static int parse_emit(const ParseCfg &cfg, const uint8_t *d_enc, const uint32_t *d_lo, size_t n, ParsePlan &pp,
+                      uint8_t *d_dst, cudaStream_t s) {
+    RSN_LAUNCH(k_emit_write, (unsigned)pp.blocks, kPT, 0, s, cfg, d_enc, d_lo, n, pp.vis.as<uint16_t>(),
+               pp.bo.as<uint64_t>(), d_dst);
+    return RSN_OK;
+}
+
+static int parse_and_emit(const uint8_t *d_enc, size_t n, ParseCfg cfg, const uint32_t *d_lo, uint8_t **d_out,
+                          size_t *out_n, cudaStream_t s) {
+    ParsePlan pp;
+    RSN_TRY(parse_build_tables(cfg, d_lo, n, pp, s));
     uint64_t total = 0;
-    RSN_TRY(read_u64(bo.as<uint64_t>() + blocks, &total, s));
+    RSN_TRY(parse_resolve(cfg, d_lo, n, 0, pp, &total, s));
     DevBuf out;
     RSN_TRY(out.alloc_out(total + 16, s));
-    RSN_LAUNCH(k_emit_write, (unsigned)blocks, kPT, 0, s, cfg, d_enc, d_lo, n, vis.as<uint16_t>(), bo.as<uint64_t>(),
-               out.as<uint8_t>());
+    RSN_TRY(parse_emit(cfg, d_enc, d_lo, n, pp, out.as<uint8_t>(), s));
     *d_out = (uint8_t *)out.release();
     *out_n = (size_t)total;
     return RSN_OK;
@@ -939,6 +984,244 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     RSN_LAUNCH(kb_emit_write, dim3((unsigned)blocks_cap, g), kPT, 0, s, b, outp.as<uint8_t *>());
     RSN_CUDA(cudaStreamSynchronize(s));  // h_outp is read by the copy above
     out.owned.push_back(res.release());
+    return RSN_OK;
+}
+
+// ============================================================================= one stream over several GPUs
+//
+// BASELINE configs[4]: a single large stream whose match search is sharded by position range.  One
+// host thread and stream per shard (shard g runs on device g mod the device count, so the whole
+// scheme can be exercised on one GPU):
+//   1. every shard uploads and escapes its range of the INPUT; the escaped lengths give the global
+//      escaped offsets;
+//   2. the escaped stream is re-cut into ranges of whole 4096-position parse blocks, and every shard
+//      assembles its range plus a window of bytes before it (the search buffer of lzss.go:123-129) and
+//      a window after it (a match is at most W long) — peer copies from whichever shards hold them;
+//      with no escapes that is just the two halos, 2 x W bytes per shard;
+//   3. match search over the slice; exit tables of the owned range; the table of where the orbit of
+//      lzss.go:134-151 leaves the shard for each of the J + 1 possible entry offsets (8 KB) goes to the
+//      host, which composes them into every shard's true entry;
+//   4. every shard resolves its orbit from its entry, emits locally and copies its part of the output
+//      straight into the (pinned) result buffer at its offset.
+// No match array leaves its GPU; GPU-to-GPU traffic is the slices' halos.
+namespace {
+
+class Barrier {
+  public:
+    explicit Barrier(int n) : n_(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
+        const uint64_t gen = gen_;
+        if (++count_ == n_) {
+            count_ = 0;
+            gen_++;
+            cv_.notify_all();
+        } else {
+            cv_.wait(lk, [&] { return gen_ != gen; });
+        }
+    }
+
+  private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_, count_ = 0;
+    uint64_t gen_ = 0;
+};
+
+struct Sharded {
+    int shards = 0, ndev = 1;
+    const uint8_t *in = nullptr;
+    size_t n = 0;
+    int64_t window = 0;
+    std::vector<size_t> a;                  // input range of shard g: [a[g], a[g+1])
+    std::vector<const uint8_t *> enc;       // its escaped bytes (device memory of device g mod ndev)
+    std::vector<size_t> A;                  // global escaped offset of those bytes: [A[g], A[g+1])
+    size_t en = 0;
+    uint32_t W = 0;
+    std::vector<size_t> S;                  // escaped range OWNED by shard g: [S[g], S[g+1]), whole parse blocks
+    std::vector<HostVec<uint16_t>> exits;   // [g][0..J]
+    std::vector<size_t> entry;              // where the orbit enters shard g, relative to S[g]
+    std::vector<uint64_t> total, O;         // output bytes and output offset of shard g
+    uint8_t *h_out = nullptr;
+    std::atomic<int> rc{RSN_OK};
+    std::atomic<uint64_t> peer_bytes{0};
+    Barrier bar;
+    explicit Sharded(int k) : bar(k) {}
+    void fail(int code) {
+        int expect = RSN_OK;
+        if (code != RSN_OK) rc.compare_exchange_strong(expect, code);
+    }
+    bool ok() const { return rc.load() == RSN_OK; }
+};
+
+thread_local uint64_t g_last_peer_bytes = 0;
+
+int shard_upload_escape(Sharded &sh, int g, DevBuf &d_in, DevBuf &enc_buf, cudaStream_t s) {
+    const size_t len = sh.a[g + 1] - sh.a[g];
+    RSN_TRY(d_in.alloc(len + 64, s));
+    if (len) RSN_CUDA(cudaMemcpyAsync(d_in.p, sh.in + sh.a[g], len, cudaMemcpyHostToDevice, s));
+    const uint8_t *e = nullptr;
+    size_t en = 0;
+    RSN_TRY(lzss_escape(d_in.as<uint8_t>(), len, enc_buf, &e, &en, s));
+    RSN_CUDA(cudaStreamSynchronize(s));
+    sh.enc[g] = e;
+    sh.A[g + 1] = en;  // lengths for now; prefix-summed by shard 0
+    return RSN_OK;
+}
+
+int shard_assemble(Sharded &sh, int g, size_t lo, size_t hi, DevBuf &slice, cudaStream_t s) {
+    RSN_TRY(slice.alloc(hi - lo + 64, s));
+    const int mydev = g % sh.ndev;
+    for (int h = 0; h < sh.shards; h++) {
+        const size_t x = std::max(lo, sh.A[h]), y = std::min(hi, sh.A[h + 1]);
+        if (x >= y) continue;
+        uint8_t *dst = slice.as<uint8_t>() + (x - lo);
+        const uint8_t *src = sh.enc[h] + (x - sh.A[h]);
+        const int hdev = h % sh.ndev;
+        if (hdev == mydev) {
+            RSN_CUDA(cudaMemcpyAsync(dst, src, y - x, cudaMemcpyDeviceToDevice, s));
+        } else {
+            RSN_CUDA(cudaMemcpyPeerAsync(dst, mydev, src, hdev, y - x, s));
+            sh.peer_bytes.fetch_add(y - x);
+        }
+    }
+    RSN_CUDA(cudaStreamSynchronize(s));  // the sources belong to other threads' arenas: done before the next barrier
+    return RSN_OK;
+}
+
+void shard_thread(Sharded &sh, int g) {
+    const int dev = g % sh.ndev;
+    int rc = rsn_init(dev);
+    sh.fail(rc);
+    cudaStream_t s = rc == RSN_OK ? ctx().own_stream : nullptr;
+    if (rc == RSN_OK && sh.ndev > 1) {
+        for (int d = 0; d < sh.ndev; d++)
+            if (d != dev && cudaDeviceEnablePeerAccess(d, 0) != cudaSuccess) cudaGetLastError();  // already on / unsupported: copies still work
+    }
+    ArenaScope scope(s);
+    DevBuf d_in, enc_buf, slice, packed, dex, d_out;
+    ParsePlan pp;
+    // ---- 1. upload, escape, global escaped offsets
+    if (sh.ok()) sh.fail(shard_upload_escape(sh, g, d_in, enc_buf, s));
+    sh.bar.wait();
+    if (g == 0 && sh.ok()) {
+        for (int k = 0; k < sh.shards; k++) sh.A[k + 1] += sh.A[k];
+        sh.en = sh.A[sh.shards];
+        if (sh.en) sh.fail(lzss_effective_window(sh.window, sh.en, &sh.W));
+        const size_t per = div_up(div_up(sh.en, (size_t)sh.shards), kPB) * kPB;
+        for (int k = 0; k <= sh.shards; k++) sh.S[k] = std::min(sh.en, (size_t)k * per);
+    }
+    sh.bar.wait();
+    // ---- 2. the shard's slice of the escaped stream: a window before, the owned range, a window after
+    const uint32_t W = sh.W, J = W;
+    const size_t n_own = sh.S[g + 1] - sh.S[g];
+    const size_t W4 = ((size_t)W + 3) & ~(size_t)3;  // keeps the owned records 16-byte aligned
+    const size_t lo = sh.S[g] > W4 ? sh.S[g] - W4 : 0, hi = std::min(sh.en, sh.S[g + 1] + W);
+    const size_t own_at = sh.S[g] - lo;
+    if (sh.ok() && n_own) sh.fail(shard_assemble(sh, g, lo, hi, slice, s));
+    sh.bar.wait();
+    // ---- 3. match search, exit tables, exits for every entry offset
+    const ParseCfg cfg{W, J, RSN_LZSS_ASYNC, nullptr};
+    const uint32_t *d_lo = nullptr;
+    const uint8_t *d_enc = nullptr;
+    auto step3 = [&]() -> int {
+        HostVec<uint16_t> &ex = sh.exits[g];
+        if (!ex.resize((size_t)J + 1)) return RSN_ERR_NOMEM;
+        if (n_own == 0) {  // nothing owned: the orbit passes through
+            for (uint32_t r = 0; r <= J; r++) ex[r] = (uint16_t)r;
+            return RSN_OK;
+        }
+        const size_t sn = hi - lo;
+        RSN_TRY(packed.alloc(div_up(sn, kPB) * kPB * 4 + 64, s));
+        RSN_TRY(lzss_match(slice.as<uint8_t>(), sn, W, packed.as<uint32_t>(), s));
+        d_lo = packed.as<uint32_t>() + own_at;
+        d_enc = slice.as<uint8_t>() + own_at;
+        RSN_TRY(parse_build_tables(cfg, d_lo, n_own, pp, s));
+        RSN_TRY(dex.alloc(((size_t)J + 1) * 2, s));
+        RSN_LAUNCH(k_shard_exits, (unsigned)div_up((size_t)J + 1, 256), 256, 0, s, pp.E0.as<uint16_t>(),
+                   pp.T[pp.lv.top].as<uint16_t>(), pp.lv.top, pp.lv.rsize[pp.lv.top], J, n_own, dex.as<uint16_t>());
+        RSN_CUDA(cudaMemcpyAsync(ex.data(), dex.p, ((size_t)J + 1) * 2, cudaMemcpyDeviceToHost, s));
+        RSN_CUDA(cudaStreamSynchronize(s));
+        return RSN_OK;
+    };
+    if (sh.ok()) sh.fail(step3());
+    sh.bar.wait();
+    if (g == 0 && sh.ok()) {  // compose: the exit of one shard is the entry of the next
+        size_t e = 0;
+        for (int k = 0; k < sh.shards; k++) {
+            sh.entry[k] = e;
+            e = sh.exits[k][e];
+        }
+    }
+    sh.bar.wait();
+    // ---- 4. the orbit from the true entry, sizes, emit into the result at the shard's offset
+    if (sh.ok() && n_own) sh.fail(parse_resolve(cfg, d_lo, n_own, sh.entry[g], pp, &sh.total[g], s));
+    sh.bar.wait();
+    if (g == 0 && sh.ok()) {
+        uint64_t at = 0;
+        for (int k = 0; k < sh.shards; k++) {
+            sh.O[k] = at;
+            at += sh.total[k];
+        }
+        sh.O[sh.shards] = at;
+        sh.h_out = (uint8_t *)host_out_alloc(at ? at : 1);
+        if (!sh.h_out) sh.fail(RSN_ERR_NOMEM);
+    }
+    sh.bar.wait();
+    auto step4 = [&]() -> int {
+        if (!n_own || !sh.total[g]) return RSN_OK;
+        RSN_TRY(d_out.alloc(sh.total[g] + 16, s));
+        RSN_TRY(parse_emit(cfg, d_enc, d_lo, n_own, pp, d_out.as<uint8_t>(), s));
+        RSN_CUDA(cudaMemcpyAsync(sh.h_out + sh.O[g], d_out.p, sh.total[g], cudaMemcpyDeviceToHost, s));
+        RSN_CUDA(cudaStreamSynchronize(s));
+        return RSN_OK;
+    };
+    if (sh.ok()) sh.fail(step4());
+    if (s) cudaStreamSynchronize(s);
+    sh.bar.wait();  // nobody rewinds its arena while another shard may still read from it
+}
+
+}  // namespace
+
+uint64_t lzss_sharded_last_peer_bytes() { return g_last_peer_bytes; }
+
+// lz.CompressAsync (lzss.go:109-154) of one host buffer over `shards` shards (see above).
+int lzss_compress_sharded(const uint8_t *in, size_t n, int64_t window, int shards, uint8_t **out, size_t *out_n) {
+    int ndev = 0;
+    RSN_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return RSN_ERR_NO_DEVICE;
+    if (shards < 1 || shards > 64) return RSN_ERR_INVALID_ARG;
+    Sharded sh(shards);
+    sh.shards = shards;
+    sh.ndev = ndev;
+    sh.in = in;
+    sh.n = n;
+    sh.window = window;
+    sh.a.resize(shards + 1);
+    for (int g = 0; g <= shards; g++) sh.a[g] = (size_t)((unsigned __int128)n * g / shards);
+    sh.enc.assign(shards, nullptr);
+    sh.A.assign(shards + 1, 0);
+    sh.S.assign(shards + 1, 0);
+    sh.exits = std::vector<HostVec<uint16_t>>(shards);
+    sh.entry.assign(shards, 0);
+    sh.total.assign(shards, 0);
+    sh.O.assign(shards + 1, 0);
+    std::vector<std::thread> th;
+    for (int g = 1; g < shards; g++) th.emplace_back(shard_thread, std::ref(sh), g);
+    {
+        // shard 0 runs on the calling thread; its context goes back to the device it had
+        const int prev = ctx().ready ? ctx().device : -1;
+        shard_thread(sh, 0);
+        if (prev >= 0 && prev != ctx().device) rsn_init(prev);
+    }
+    for (auto &t : th) t.join();
+    g_last_peer_bytes = sh.peer_bytes.load();
+    if (!sh.ok()) {
+        if (sh.h_out) rsn_free(sh.h_out);
+        return sh.rc.load();
+    }
+    *out = sh.h_out;
+    *out_n = (size_t)sh.O[shards];
     return RSN_OK;
 }
 

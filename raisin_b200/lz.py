@@ -24,6 +24,13 @@ def Compress(fileContents, useProgressBar: bool = False, maxSearchBufferLength: 
     return _lib.call_host(_lib.lib().rsn_lzss_compress, fileContents, int(maxSearchBufferLength), RSN_LZSS_ITER)
 
 
+def CompressAsyncSharded(fileContents, ngpus: int, maxSearchBufferLength: int = DefaultWindowSize) -> bytes:
+    """CompressAsync of one stream with the match search sharded by position range over `ngpus`
+    shards (BASELINE configs[4]); byte-identical to CompressAsync."""
+    return _lib.call_host(_lib.lib().rsn_lzss_compress_sharded, fileContents, int(maxSearchBufferLength), RSN_LZSS_ASYNC,
+                          int(ngpus))
+
+
 def Decompress(fileContents, useProgressBar: bool = False) -> bytes:
     return _lib.call_host(_lib.lib().rsn_lzss_decompress, fileContents)
 

@@ -170,3 +170,37 @@ def repetitive(n: int, seed: int = 5, motif: int = 2048) -> bytes:
     where = where[where < n]
     buf[where] = (rng.integers(0x61, 0x7B, size=where.size)).astype(np.uint8)
     return buf.tobytes()
+
+
+def config5_into(buf: "np.ndarray", seed: int = 5, motif_len: int = 3000) -> None:
+    """BASELINE config 5 stream written into `buf` (uint8): a text motif repeated, one byte mutated
+    about every 64 KiB and 1 KiB of fresh text laid over the stream once per MiB, so that L saturates
+    for almost every position.  SURVEY 8(d) proposes a 64 KiB motif, but a repeat further back than
+    the 4096-byte search buffer can never be referenced (lzss.go:123-129) and such a stream is not
+    repetitive to this codec at all (8 MiB of it compress to 91 %); the motif is 3000 bytes instead."""
+    n = buf.size
+    motif = np.frombuffer(text(motif_len, seed), dtype=np.uint8)
+    full = (n // motif_len) * motif_len
+    if full:
+        buf[:full].reshape(-1, motif_len)[:] = motif
+    if n > full:
+        buf[full:] = motif[: n - full]
+    rng = np.random.default_rng(seed)
+    spans = -(-n // 65536)
+    where = np.arange(spans, dtype=np.int64) * 65536 + rng.integers(0, 65536, size=spans)
+    where = where[where < n]
+    buf[where] = rng.integers(0x61, 0x7B, size=where.size).astype(np.uint8)
+    mib = n >> 20
+    if mib:
+        fresh = np.frombuffer(text(min(mib, 4096) * 1024, seed + 1), dtype=np.uint8)
+        for k in range(mib):
+            at = (k << 20) + 300 + 37 * (k % 1000)
+            src = (k % 4096) * 1024
+            if at + 1024 <= n:
+                buf[at:at + 1024] = fresh[src:src + 1024]
+
+
+def config5(n: int, seed: int = 5) -> bytes:
+    out = np.empty(n, dtype=np.uint8)
+    config5_into(out, seed)
+    return out.tobytes()

@@ -65,3 +65,29 @@ def test_sharded_compress_matches_oracle(rsn, oracle, world, variant):
         lib.rsn_dev_free(out, sp)
     want = oracle.lzss_compress_async(data, 4096, threads=8) if variant == 0 else oracle.lzss_compress_iter(data, 4096)
     assert bytes(hb) == want
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_c_abi_matches_single_gpu(rsn, oracle, shards):
+    """rsn_lzss_compress_sharded (BASELINE configs[4] behind the C ABI): one host thread per shard,
+    shard g on device g mod the device count, so this runs on a single GPU as well.  Same bytes as the
+    single-GPU call and the oracle, for data with and without escapes, ragged sizes, and inputs too
+    small to give every shard a parse block."""
+    cases_ = {
+        "text": synth.text(300000, 31),
+        "logs_with_escapes": synth.logs(250000, 32),
+        "repetitive": synth.repetitive(400000, 33, motif=1500),
+        "escape_heavy": (b"<\\\xff" * 30000) + synth.text(50000, 34),
+        "runs": b"a" * 100000 + b"b" * 50001,
+        "small": synth.text(5000, 35),
+        "tiny": b"abcabcabc",
+        "empty": b"",
+    }
+    for name, data in cases_.items():
+        got = rsn.lz.CompressAsyncSharded(data, shards)
+        assert got == rsn.lz.CompressAsync(data), (name, shards)
+        assert got == oracle.lzss_compress_async(data, 4096, threads=8), (name, shards)
+    for w in (100, 1024):
+        data = cases_["logs_with_escapes"]
+        got = rsn._lib.call_host(rsn._lib.lib().rsn_lzss_compress_sharded, data, w, 0, shards)
+        assert got == oracle.lzss_compress_async(data, w, threads=8), (w, shards)
