@@ -84,7 +84,11 @@ def _take(rc, out, out_n) -> bytes:
     if rc != 0:
         raise OracleError(rc)
     try:
-        return C.string_at(out, out_n.value)
+        n = out_n.value
+        if n < (1 << 31) - 1:
+            return C.string_at(out, n)
+        # ctypes.string_at takes a C int
+        return bytes((C.c_ubyte * n).from_address(C.cast(out, C.c_void_p).value))
     finally:
         lib().rsno_free(out)
 

@@ -9,6 +9,8 @@
 // tables the encode / decode kernels read.  huff_host.cpp remains the single-stream implementation;
 // both are checked against the oracle.
 #include "common.cuh"
+
+#include <algorithm>
 #include "huff.cuh"
 
 namespace rsn {
@@ -17,51 +19,132 @@ namespace {
 
 constexpr int kLutBitsTree = 12;  // == kLutBits in huff_decode.cu
 
-// heap entry = (frequency sum << 32) | node: Less compares the high words only (huffman.go:43-45)
-__device__ __forceinline__ bool heap_less(uint64_t a, uint64_t b) { return (uint32_t)(a >> 32) < (uint32_t)(b >> 32); }
+// Heap entry = (frequency sum << SH) | node; Less compares the frequency sums only (huffman.go:43-45).
+// Two layouts: 64-bit entries with SH = 32 for any file, and 32-bit entries with SH = 13 for files of
+// fewer than 2^19 runes and fewer than 4096 leaves (every file of up to 512 KiB) — the replay is one
+// lane following a chain of dependent shared-memory loads and integer operations, and 32-bit entries
+// take about a third of the instructions out of that chain.
+template <typename E, int SH>
+struct HeapOps {
+    static __device__ __forceinline__ bool less(E a, E b) { return (a >> SH) < (b >> SH); }
+    // container/heap.down / up (Go 1.15) with the moving element carried in a register: the array
+    // ends up exactly as after Go's swaps.
+    static __device__ __forceinline__ void down(E *h, int i, int n) {
+        const E v = h[i];
+        for (;;) {
+            const int j1 = 2 * i + 1;
+            if (j1 >= n) break;
+            const int j2 = j1 + 1 < n ? j1 + 1 : j1;
+            const E a = h[j1], b = h[j2];
+            const bool right = less(b, a);  // j2 == j1 gives false
+            const E c = right ? b : a;
+            if (!less(c, v)) break;
+            h[i] = c;
+            i = right ? j2 : j1;
+        }
+        h[i] = v;
+    }
+    static __device__ __forceinline__ void up(E *h, int j) {
+        const E v = h[j];
+        while (j > 0) {
+            const int i = (j - 1) / 2;
+            if (!less(v, h[i])) break;
+            h[j] = h[i];
+            j = i;
+        }
+        h[j] = v;
+    }
+    // heap.Init, then a = Pop(), b = Pop(), Push(a + b) until one node is left (huffman.go:88-102)
+    static __device__ __forceinline__ int replay(E *heap, int k, HuffNodeDev *nodes, uint32_t *parent) {
+        int n = k;
+        for (int i = n / 2 - 1; i >= 0; i--) down(heap, i, n);
+        int next = k;
+        const E node_mask = ((E)1 << SH) - 1;
+        while (n > 1) {
+            // Pop: swap root and last, sift the new root over the shorter heap
+            const E a = heap[0];
+            heap[0] = heap[--n];
+            down(heap, 0, n);
+            const E b = heap[0];
+            heap[0] = heap[--n];
+            if (n > 0) down(heap, 0, n);
+            const uint32_t an = (uint32_t)(a & node_mask), bn = (uint32_t)(b & node_mask);
+            nodes[next] = HuffNodeDev{(int32_t)an, (int32_t)bn};  // left = first popped (huffman.go:96-99)
+            parent[an] = (uint32_t)next;
+            parent[bn] = (uint32_t)next | 0x80000000u;
+            heap[n] = (((a >> SH) + (b >> SH)) << SH) | (E)next;  // Push (the sums fit: checked by the caller)
+            up(heap, n);
+            n++;
+            next++;
+        }
+        return (int)(uint32_t)(heap[0] & node_mask);
+    }
+};
 
-// container/heap.down / up (Go 1.15) with the moving element carried in a register: the array ends
-// up exactly as after Go's swaps.
-// Two levels per round trip to shared memory: the four grandchildren are loaded together with the two
-// children, so the second comparison does not wait for another load (the replay is a chain of
-// dependent loads, and one lane per file runs it).
-__device__ __forceinline__ void heap_down(uint64_t *h, int i, int n) {
-    const uint64_t v = h[i];
-    for (;;) {
-        const int j1 = 2 * i + 1;
-        if (j1 >= n) break;
-        const int j2 = j1 + 1 < n ? j1 + 1 : j1;
-        const int g = 2 * j1 + 1;  // grandchildren g .. g+3 (children of j1, then of j1+1)
-        const uint64_t a = h[j1], b = h[j2];
-        const uint64_t g0 = g < n ? h[g] : 0, g1 = g + 1 < n ? h[g + 1] : 0, g2 = g + 2 < n ? h[g + 2] : 0,
-                       g3 = g + 3 < n ? h[g + 3] : 0;
-        const bool right = heap_less(b, a);  // j2 == j1 gives false
-        const uint64_t c = right ? b : a;
-        if (!heap_less(c, v)) break;
-        h[i] = c;
-        i = right ? j2 : j1;
-        // second level from the prefetched values
-        const int k1 = 2 * i + 1;
-        if (k1 >= n) break;
-        const bool has2 = k1 + 1 < n;
-        const uint64_t a2 = right ? g2 : g0, b2 = has2 ? (right ? g3 : g1) : a2;
-        const bool right2 = heap_less(b2, a2);
-        const uint64_t c2 = right2 ? b2 : a2;
-        if (!heap_less(c2, v)) break;
-        h[i] = c2;
-        i = right2 ? k1 + 1 : k1;
+// The same replay for files of fewer than 2^19 runes and fewer than 2^DEPTH leaves, arranged for the
+// one lane that runs it: 32-bit entries (frequency << 13 | node); the array starts one word into an
+// 8-byte aligned buffer so that both children of a node come with ONE 8-byte load; every slot past
+// the heap's end holds an all-ones sentinel (nothing is smaller), so a level of the sift is just
+// address -> load -> compare -> select, with no bounds tests and no branch; where the sinking element
+// stops is settled afterwards from the keys collected on the way.  The array ends up exactly as after
+// container/heap's swaps.  hp must hold 2^(DEPTH+1) entries.
+constexpr uint32_t kSent = 0xFFFFFFFFu;
+__device__ __forceinline__ bool less13(uint32_t a, uint32_t b) { return (a >> 13) < (b >> 13); }
+
+template <int DEPTH>
+__device__ __forceinline__ void down_root_small(uint32_t *hp) {
+    const uint32_t v = hp[0];
+    int idx[DEPTH + 1];
+    uint32_t key[DEPTH];
+    idx[0] = 0;
+#pragma unroll
+    for (int l = 0; l < DEPTH; l++) {
+        const int j1 = 2 * idx[l] + 1;
+        const uint2 ab = *reinterpret_cast<const uint2 *>(hp + j1);  // children j1, j1 + 1
+        const bool right = less13(ab.y, ab.x);                     // a missing right child is a sentinel: false
+        key[l] = right ? ab.y : ab.x;
+        idx[l + 1] = j1 + (right ? 1 : 0);
     }
-    h[i] = v;
+    bool going = true;
+    int stop = 0;
+#pragma unroll
+    for (int l = 0; l < DEPTH; l++) {
+        going = going && less13(key[l], v);  // Go: if !less(j, i) break
+        if (going) {
+            hp[idx[l]] = key[l];
+            stop = idx[l + 1];
+        }
+    }
+    hp[stop] = v;
 }
-__device__ __forceinline__ void heap_up(uint64_t *h, int j) {
-    const uint64_t v = h[j];
-    while (j > 0) {
-        const int i = (j - 1) / 2;
-        if (!heap_less(v, h[i])) break;
-        h[j] = h[i];
-        j = i;
+
+template <int DEPTH>
+__device__ __forceinline__ int replay_small(uint32_t *hp, int k, HuffNodeDev *nodes, uint32_t *parent) {
+    int n = k;
+    for (int i = n / 2 - 1; i >= 0; i--) HeapOps<uint32_t, 13>::down(hp, i, n);  // heap.Init
+    int next = k;
+    while (n > 1) {
+        // Pop: the last element replaces the root and sinks over the shorter heap
+        const uint32_t a = hp[0];
+        --n;
+        hp[0] = hp[n];
+        hp[n] = kSent;
+        down_root_small<DEPTH>(hp);
+        const uint32_t b = hp[0];
+        --n;
+        hp[0] = hp[n];
+        hp[n] = kSent;
+        if (n > 0) down_root_small<DEPTH>(hp);
+        const uint32_t an = a & 0x1FFFu, bn = b & 0x1FFFu;
+        nodes[next] = HuffNodeDev{(int32_t)an, (int32_t)bn};  // left = first popped (huffman.go:96-99)
+        parent[an] = (uint32_t)next;
+        parent[bn] = (uint32_t)next | 0x80000000u;
+        hp[n] = (((a >> 13) + (b >> 13)) << 13) | (uint32_t)next;  // Push
+        HeapOps<uint32_t, 13>::up(hp, n);
+        n++;
+        next++;
     }
-    h[j] = v;
+    return (int)(hp[0] & 0x1FFFu);
 }
 
 __global__ void __launch_bounds__(32) kb_huff_tree(TreeJob *__restrict__ jobs) {
@@ -72,34 +155,24 @@ __global__ void __launch_bounds__(32) kb_huff_tree(TreeJob *__restrict__ jobs) {
     const unsigned lane = threadIdx.x;
     HuffNodeDev *nodes = job.nodes;
     uint32_t *parent = job.parent;
-    for (int i = lane; i < k; i += 32) {
-        heap[i] = ((uint64_t)job.freq[i] << 32) | (uint64_t)i;
-        nodes[i] = HuffNodeDev{-1, (int32_t)job.rune[i]};
+    // 32-bit entries when the sums and the node numbers fit 19 + 13 bits
+    uint32_t fsum = 0;
+    for (int i = lane; i < k; i += 32) fsum += job.freq[i] < (1u << 19) ? job.freq[i] : (1u << 19);
+    for (int d = 16; d; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+    const bool small = k < 4096 && fsum < (1u << 19);
+    uint32_t *hp = reinterpret_cast<uint32_t *>(heap) + 1;  // children pairs 8-byte aligned
+    const int slots = small ? (k <= 255 ? 512 : 8192) : 0;
+    for (int i = lane; i < max(k, slots); i += 32) {
+        if (small) hp[i] = i < k ? ((job.freq[i] << 13) | (uint32_t)i) : kSent;
+        else heap[i] = ((uint64_t)job.freq[i] << 32) | (uint64_t)i;
+        if (i < k) nodes[i] = HuffNodeDev{-1, (int32_t)job.rune[i]};
     }
     __syncwarp();
     int root = 0;
     if (lane == 0) {
-        int n = k;
-        for (int i = n / 2 - 1; i >= 0; i--) heap_down(heap, i, n);  // heap.Init
-        int next = k;
-        while (n > 1) {
-            // a = Pop(), b = Pop(): swap root and last, sift the new root over the shorter heap
-            const uint64_t a = heap[0];
-            heap[0] = heap[--n];
-            heap_down(heap, 0, n);
-            const uint64_t b = heap[0];
-            heap[0] = heap[--n];
-            if (n > 0) heap_down(heap, 0, n);
-            const uint32_t an = (uint32_t)a, bn = (uint32_t)b;
-            nodes[next] = HuffNodeDev{(int32_t)an, (int32_t)bn};  // left = first popped (huffman.go:96-99)
-            parent[an] = (uint32_t)next;
-            parent[bn] = (uint32_t)next | 0x80000000u;
-            heap[n] = (((a >> 32) + (b >> 32)) << 32) | (uint64_t)next;  // Push (sums stay below 2^32: checked by the host)
-            heap_up(heap, n);
-            n++;
-            next++;
-        }
-        root = (int)(uint32_t)heap[0];
+        if (!small) root = HeapOps<uint64_t, 32>::replay(heap, k, nodes, parent);
+        else if (k <= 255) root = replay_small<8>(hp, k, nodes, parent);  // text-like alphabets
+        else root = replay_small<12>(hp, k, nodes, parent);
         job.root = root;
     }
     root = __shfl_sync(0xffffffffu, root, 0);
@@ -164,7 +237,8 @@ __global__ void __launch_bounds__(32) kb_huff_tree(TreeJob *__restrict__ jobs) {
 int huff_tree_batch(TreeJob *d_jobs, size_t G, uint32_t kmax, cudaStream_t s) {
     if (G == 0) return RSN_OK;
     if (kmax > kTreeMaxLeaves) return RSN_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)(kmax ? kmax : 1) * 8;
+    // 64-bit entries: kmax * 8 bytes; the 32-bit layout pads to 512 or 8192 entries (+ 1 word)
+    const size_t smem = std::max<size_t>((size_t)(kmax ? kmax : 1) * 8, kmax <= 255 ? 513 * 4 + 12 : 8193 * 4 + 12);
     static thread_local size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         RSN_CUDA(cudaFuncSetAttribute(kb_huff_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTreeMaxLeaves * 8)));
