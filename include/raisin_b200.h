@@ -106,7 +106,7 @@ int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, u
  * Batches of independent files (BASELINE configs[3]; what engine.BenchmarkSuite's per-file loop does,
  * engine.go:208-262): file i is compressed (or decompressed) with the layer list exactly as
  * rsn_compress_layers would.  Host buffers (device == 0): files of up to 4 MiB are cut into groups
- * of about 64 MiB and every kernel of a stage runs once per group (the file index is a grid
+ * of up to 64 MiB and every kernel of a stage runs once per group (the file index is a grid
  * dimension), so a small file costs no kernel launches or synchronisations of its own; groups, and
  * the files that go one by one (empty, larger than 4 MiB), are spread over `workers` host threads
  * (0 = default), each with its own CUDA stream.  out[i]/out_n[i] receive library-owned buffers
@@ -123,7 +123,8 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
  * The grouping rsn_batch_layers applies to host-buffer files of these sizes (host logic only; needs
  * no device): group_of[i] = index of the group file i travels in, or -1 for the per-file path
  * (empty files, files above 4 MiB).  A group holds files of one size class (within a factor of
- * two of each other; everything below 4 KiB is one class), at most 2048 files and about 64 MiB.
+ * two of each other; everything below 4 KiB is one class), at most 2048 files and at most 64 MiB
+ * (less for small batches: total / workers, but at least 16 MiB, so that every worker gets a group).
  */
 int rsn_batch_plan(size_t count, const size_t *in_n, int64_t *group_of, size_t *n_groups);
 

@@ -26,7 +26,7 @@ static int to_host(uint8_t *d, size_t n, uint8_t **out, size_t *out_n, cudaStrea
     }
     cudaError_t e = cudaSuccess;
     if (n) e = cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = stream_wait(s);
     out_free(d, s);
     if (e != cudaSuccess) {
         rsn_free(h);
@@ -303,12 +303,18 @@ namespace rsn {
 // memory stays proportional to the bytes in the group whatever the mix of sizes.  `in` may be null
 // (planning only).
 void batch_plan(size_t count, const uint8_t *const *in, const size_t *in_n, int device,
-                std::vector<std::vector<size_t>> &groups, std::vector<size_t> &singles) {
-    // 64 MiB groups: the per-group costs that do not shrink with the group (the serial heap replay of
-    // the Huffman tree kernel, ~4 ms for a file of random bytes, and a handful of host
+                std::vector<std::vector<size_t>> &groups, std::vector<size_t> &singles, int workers = 8) {
+    // Up to 64 MiB per group: the per-group costs that do not shrink with the group (the serial heap
+    // replay of the Huffman tree kernel, 2-4 ms for a file of random bytes, and a handful of host
     // synchronisations per stage) are paid 16 times per GiB instead of 64 (2048 config-4 files:
-    // 3.6 GB/s with 16 MiB groups, 4.4 GB/s with 64 MiB, 8 workers)
-    size_t group_bytes = (size_t)64 << 20;
+    // 3.6 GB/s with 16 MiB groups, 4.4 GB/s with 64 MiB, 8 workers).  Small batches are cut finer so
+    // that every worker still gets a group (a rank's share of a batch split over 8 GPUs), but not
+    // below 16 MiB (512 files: 38 ms per pass with 8 MiB groups, 34 ms with 16 MiB).
+    size_t total_bytes = 0;
+    for (size_t i = 0; i < count; i++)
+        if (in_n[i] <= kBatchMaxFile) total_bytes += in_n[i];
+    size_t group_bytes = total_bytes / (size_t)(workers > 0 ? workers : 1);
+    group_bytes = std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)16 << 20, group_bytes));
     size_t kGroupFiles = 2048;
     if (const char *e = getenv("RSN_BATCH_GROUP_MIB")) {  // tuning knobs
         const long v = atol(e);
@@ -447,7 +453,7 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
         }
         off += (in_n[i] + 64 + 255) & ~(size_t)255;
     }
-    if (h_stage) RSN_CUDA(cudaStreamSynchronize(s));
+    if (h_stage) RSN_CUDA(stream_wait(s));
     const bool have_host = !device || h_stage != nullptr;
     tr.mark(device ? "stage" : "h2d");
     const size_t k = algos.size();
@@ -495,7 +501,7 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
         RSN_TRY(dj.alloc(G * sizeof(CopyJob), s));
         RSN_CUDA(cudaMemcpyAsync(dj.p, jobs.data(), G * sizeof(CopyJob), cudaMemcpyHostToDevice, s));
         if (cap) RSN_LAUNCH(kb_copy_out, dim3((unsigned)div_up(cap, 16384), (unsigned)G), 256, 0, s, dj.as<CopyJob>());
-        cudaError_t e = cudaStreamSynchronize(s);  // `jobs` is read by the copy above
+        cudaError_t e = stream_wait(s);  // `jobs` is read by the copy above
         if (e != cudaSuccess) rc = cuda_fail(e, "batch copy-out sync", __FILE__, __LINE__);
         cur.release(s);
         tr.mark("copy out");
@@ -522,7 +528,7 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
         out[i] = h;
         out_n[i] = cur.n[f];
     }
-    cudaError_t e = cudaStreamSynchronize(s);
+    cudaError_t e = stream_wait(s);
     if (e != cudaSuccess) rc = cuda_fail(e, "batch d2h sync", __FILE__, __LINE__);
     cur.release(s);
     tr.mark("d2h");
@@ -567,7 +573,7 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
     }
     std::vector<std::vector<size_t>> groups;
     std::vector<size_t> singles;
-    batch_plan(count, in, in_n, device, groups, singles);
+    batch_plan(count, in, in_n, device, groups, singles, workers);
     const size_t units = groups.size() + singles.size();
     if ((size_t)workers > units) workers = (int)(units ? units : 1);
     {
@@ -586,6 +592,7 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
             return;
         }
         cudaStream_t s = ctx().own_stream;
+        set_thread_blocking_sync(true);
         for (;;) {
             const size_t u = next.fetch_add(1);
             if (u >= units) break;
@@ -622,7 +629,7 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
                 if (rc == RSN_OK) rc = layers_dev(algos, compress != 0, d_in, in_n[i], &r, &rn, s);
                 if (rc == RSN_OK) {
                     if (device) {
-                        cudaStreamSynchronize(s);
+                        stream_wait(s);
                         out[i] = r;
                         out_n[i] = rn;
                     } else {
@@ -692,14 +699,14 @@ int rsn_dev_download(const void *d_src, size_t n, void *h_dst, void *stream) {
     RSN_TRY(ensure_ctx());
     cudaStream_t s = pick_stream(stream);
     if (n) RSN_CUDA(cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     return RSN_OK;
 }
 int rsn_dev_upload(const void *h_src, size_t n, void *d_dst, void *stream) {
     RSN_TRY(ensure_ctx());
     cudaStream_t s = pick_stream(stream);
     if (n) RSN_CUDA(cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     return RSN_OK;
 }
 

@@ -93,6 +93,12 @@ struct DevBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Wait for a stream.  Batch worker threads sleep on an event (cudaEventBlockingSync) instead of
+// spinning: a box runs up to 8 ranks x 8 workers, nearly all of them waiting at any moment, and
+// spinning waits starve the threads that have host work to do.  Other threads spin (lowest latency).
+cudaError_t stream_wait(cudaStream_t s);
+void set_thread_blocking_sync(bool on);
+
 // Pinned host memory from the library's pool.  Every host buffer that a cudaMemcpyAsync touches
 // must be pinned: an "async" copy to or from pageable memory waits inside the driver until the
 // stream has reached it — with the context lock held, so a device-to-host copy queued behind a 4 ms

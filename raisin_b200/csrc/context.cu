@@ -24,6 +24,32 @@ void count_launch() {
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
+// ----------------------------------------------------------------------------- stream waits
+
+namespace {
+thread_local bool t_blocking_sync = false;
+thread_local cudaEvent_t t_wait_ev = nullptr;
+thread_local int t_wait_ev_dev = -1;
+}  // namespace
+void set_thread_blocking_sync(bool on) { t_blocking_sync = on; }
+cudaError_t stream_wait(cudaStream_t s) {
+    if (!t_blocking_sync) return cudaStreamSynchronize(s);
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (!t_wait_ev || t_wait_ev_dev != dev) {
+        if (t_wait_ev) cudaEventDestroy(t_wait_ev);
+        t_wait_ev = nullptr;
+        if (cudaEventCreateWithFlags(&t_wait_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return cudaStreamSynchronize(s);
+        }
+        t_wait_ev_dev = dev;
+    }
+    cudaError_t e = cudaEventRecord(t_wait_ev, s);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(t_wait_ev);
+}
+
 // ----------------------------------------------------------------------------- per-kernel timing
 
 namespace {
@@ -491,7 +517,7 @@ int spine_scan_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t *d_total, siz
 int read_u64(const uint64_t *d_src, uint64_t *h_dst, cudaStream_t s) {
     Ctx &c = ctx();
     RSN_CUDA(cudaMemcpyAsync(c.h_scalars, d_src, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     *h_dst = c.h_scalars[0];
     return RSN_OK;
 }

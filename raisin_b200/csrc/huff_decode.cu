@@ -237,7 +237,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
         for (;;) {
             if (!h_copy.resize(take)) return RSN_ERR_NOMEM;
             RSN_CUDA(cudaMemcpyAsync(h_copy.data() + have, d_in + have, take - have, cudaMemcpyDeviceToHost, s));
-            RSN_CUDA(cudaStreamSynchronize(s));
+            RSN_CUDA(stream_wait(s));
             // the separator may straddle the previous chunk boundary: rescan from one byte before it
             const size_t from = have ? have - 1 : 0;
             const ptrdiff_t r = find_sep(h_copy.data() + from, take - from);
@@ -273,7 +273,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
         } else {
             uint8_t b = 0;
             RSN_CUDA(cudaMemcpyAsync(&b, d_in + pay_off, 1, cudaMemcpyDeviceToHost, s));
-            RSN_CUDA(cudaStreamSynchronize(s));
+            RSN_CUDA(stream_wait(s));
             diff = b;
         }
     }
@@ -290,7 +290,7 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
         const int w = utf8_encode(rootn.right, u);
         RSN_TRY(out.alloc_out(16, s));
         RSN_CUDA(cudaMemcpyAsync(out.p, u, (size_t)w, cudaMemcpyHostToDevice, s));
-        RSN_CUDA(cudaStreamSynchronize(s));
+        RSN_CUDA(stream_wait(s));
         *d_out = (uint8_t *)out.release();
         *out_n = (size_t)w;
         return RSN_OK;
@@ -621,7 +621,7 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         RSN_LAUNCH(kb_hdec_finish, (unsigned)G, 256, 0, s, files.as<HdecFile>(), cnt.as<uint64_t>(), off.as<uint64_t>());
     }
     RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HdecFile), cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     tr.mark("init+sync");
     size_t total = 0;
     for (size_t f = 0; f < G; f++) {
@@ -636,7 +636,7 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
                    res.as<uint8_t>());
         RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HdecFile), cudaMemcpyDeviceToHost, s));
     }
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     tr.mark("write");
     for (size_t f = 0; f < G; f++) {
         if (out.rc[f] != RSN_OK || plan[f].per_file) continue;

@@ -339,7 +339,7 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     HostVec<RuneFreq> h_list(k);  // pinned (see HostVec)
     if (!h_list.data()) return RSN_ERR_NOMEM;
     RSN_CUDA(cudaMemcpyAsync(h_list.data(), list.p, k * sizeof(RuneFreq), cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     list.reset();
 
     tr.mark("hist+d2h");
@@ -403,7 +403,7 @@ int huff_compress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *ou
     }
     tr.mark("encode");
     // h_codes / pre are read by async copies: wait before they go out of scope
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     *d_out = (uint8_t *)out.release();
     *out_n = total;
     return RSN_OK;
@@ -628,7 +628,7 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     if (!h_hist.data()) return RSN_ERR_NOMEM;
     RSN_CUDA(cudaMemcpyAsync(h_hist.data(), hist.p, G * kHistStride * 4, cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HencFile), cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     tr.mark("hist");
     // the per-file lists of runes >= 256, back to back in one pinned buffer
     std::vector<size_t> big_at(G + 1, 0);
@@ -640,7 +640,7 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
         RSN_CUDA(cudaMemcpyAsync(h_big.data() + big_at[f], b.big + f * b.big_stride, (size_t)h[f].big_n * 4,
                                  cudaMemcpyDeviceToHost, s));
     }
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     tr.mark("big lists d2h");
     // ---- host: leaves in the reference's order and header bytes per file; trees and codes on the
     // device, one warp per file (huff_tree.cu)
@@ -711,7 +711,7 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     RSN_CUDA(cudaMemsetAsync(dff.p, 0xFF, ff_n + 256, s));
     RSN_TRY(huff_tree_batch(djobs.as<TreeJob>(), G, kmax, s));
     RSN_CUDA(cudaMemcpyAsync(jobs.data(), djobs.p, G * sizeof(TreeJob), cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     tr.mark("device trees");
     // ---- sizes, one result buffer
     size_t total = 0;
@@ -758,7 +758,7 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     RSN_LAUNCH(kb_enc_finish, g, 256, 0, s, b);
     if (any_packed) RSN_LAUNCH(kb_enc_write<true>, tgrid, kTileThreads, 0, s, b);
     if (any_wide) RSN_LAUNCH(kb_enc_write<false>, tgrid, kTileThreads, 0, s, b);
-    RSN_CUDA(cudaStreamSynchronize(s));  // h is read by the copy above
+    RSN_CUDA(stream_wait(s));  // h is read by the copy above
     tr.mark("encode");
     for (size_t f = 0; f < G; f++) {
         if (out.rc[f] != RSN_OK || plan[f].per_file) continue;

@@ -638,7 +638,7 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
     Ctx &c = ctx();
     RSN_CUDA(cudaMemcpyAsync(c.h_scalars, toff.as<uint64_t>() + tiles, 8, cudaMemcpyDeviceToHost, s));
     RSN_CUDA(cudaMemcpyAsync(c.h_scalars + 1, err.p, 8, cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     const uint64_t sbn = c.h_scalars[0];
     const uint32_t flags = (uint32_t)c.h_scalars[1];
     if (flags & ERR_BAD_REF) return RSN_ERR_BAD_REFERENCE;
@@ -671,7 +671,7 @@ int lzss_decompress_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *
                 RSN_LAUNCH(k_resolve, (unsigned)div_up(todo, 256), 256, 0, s, sb.as<uint8_t>(), dist.as<uint32_t>(), todo,
                            wl[(round + 1) & 1].as<uint32_t>(), wl[round & 1].as<uint32_t>(), count);
             RSN_CUDA(cudaMemcpyAsync(c.h_scalars, err.p, 8, cudaMemcpyDeviceToHost, s));
-            RSN_CUDA(cudaStreamSynchronize(s));
+            RSN_CUDA(stream_wait(s));
             const uint32_t e = (uint32_t)c.h_scalars[0];
             if (e & ERR_BAD_REF) return RSN_ERR_BAD_REFERENCE;
             todo = (size_t)(uint32_t)(c.h_scalars[0] >> 32);
@@ -804,7 +804,7 @@ int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     RSN_LAUNCH(kb_tok_tile<false>, tgrid, kTileThreads, 0, s, b);
     RSN_LAUNCH(kb_tok_finish, g, 256, 0, s, b);
     RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(DecFile), cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     size_t total = 0, sb_cap = 1;
     for (size_t f = 0; f < G; f++) {
         if (h[f].n && (h[f].flags & ERR_BAD_REF)) {
@@ -893,11 +893,11 @@ int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
             RSN_LAUNCH(k_resolve, (unsigned)div_up(todo, 256), 256, 0, s, b.sb, b.dist, todo,
                        wl[(round + 1) & 1].as<uint32_t>(), wl[round & 1].as<uint32_t>(), cnt.as<uint32_t>());
         RSN_CUDA(cudaMemcpyAsync(c.h_scalars, cnt.p, 4, cudaMemcpyDeviceToHost, s));
-        RSN_CUDA(cudaStreamSynchronize(s));
+        RSN_CUDA(stream_wait(s));
         todo = (size_t)(uint32_t)c.h_scalars[0];
     }
     RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(DecFile), cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     // ---- phase C: un-escape the files whose literals hold 5C / FF
     bool any_unesc = false;
     for (size_t f = 0; f < G; f++) {
@@ -928,7 +928,7 @@ int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
         RSN_LAUNCH(kb_unesc_spine, g, 1024, 0, s, b);
         RSN_LAUNCH(kb_unesc_apply, ugrid, kTileThreads, 0, s, b);
         RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(DecFile), cudaMemcpyDeviceToHost, s));
-        RSN_CUDA(cudaStreamSynchronize(s));
+        RSN_CUDA(stream_wait(s));
     }
     for (size_t f = 0; f < G; f++) {
         if (out.rc[f] != RSN_OK) continue;

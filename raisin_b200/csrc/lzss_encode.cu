@@ -107,7 +107,7 @@ int lzss_escape(const uint8_t *d_in, size_t n, DevBuf &enc, const uint8_t **enc_
     RSN_TRY(spine_scan_u64(cnt.as<uint64_t>(), off.as<uint64_t>(), off.as<uint64_t>() + tiles, tiles, s));
     Ctx &c = ctx();
     RSN_CUDA(cudaMemcpyAsync(c.h_scalars, off.as<uint64_t>() + tiles, 16, cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     const uint64_t total = c.h_scalars[0];
     if ((uint32_t)c.h_scalars[1] == 0 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0) {
         *enc_n = n;  // identity: use the input in place
@@ -263,8 +263,7 @@ __device__ __forceinline__ size_t level_step(size_t p, int lvl, size_t rsize, co
 // T_l[r][rel] for rel in [0, J]: follow level l-1 until leaving region r (or the input).
 __device__ __forceinline__ void parse_up_body(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tprev,
                                               uint16_t *__restrict__ Tcur, int lvl, size_t rsize_prev,
-                                              size_t rsize_cur, uint32_t J, size_t n, size_t r) {
-    const uint32_t rel = blockIdx.x * blockDim.x + threadIdx.x;
+                                              size_t rsize_cur, uint32_t J, size_t n, size_t r, uint32_t rel) {
     if (rel > J) return;
     const size_t start = r * rsize_cur, end = min(start + rsize_cur, n);
     size_t p = start + rel;
@@ -274,7 +273,8 @@ __device__ __forceinline__ void parse_up_body(const uint16_t *__restrict__ E0, c
 __global__ void k_parse_up(const uint16_t *__restrict__ E0, const uint16_t *__restrict__ Tprev,
                            uint16_t *__restrict__ Tcur, int lvl, size_t rsize_prev, size_t rsize_cur, uint32_t J,
                            size_t n) {
-    parse_up_body(E0, Tprev, Tcur, lvl, rsize_prev, rsize_cur, J, n, blockIdx.y);
+    // regions along x (a stream of 8 GiB has 131072 level-1 regions; y stops at 65535)
+    parse_up_body(E0, Tprev, Tcur, lvl, rsize_prev, rsize_cur, J, n, blockIdx.x, blockIdx.y * blockDim.x + threadIdx.x);
 }
 
 // sequential walk over the (<= kFan) top-level regions
@@ -596,7 +596,7 @@ static int parse_build_tables(const ParseCfg &cfg, const uint32_t *d_lo, size_t 
     RSN_LAUNCH(k_parse_exits, (unsigned)pp.blocks, kPT, 0, s, cfg, d_lo, n, pp.E0.as<uint16_t>());
     for (int l = 1; l <= lv.top; l++) {
         RSN_TRY(pp.T[l].alloc(lv.regions[l] * (size_t)(J + 1) * 2, s));
-        dim3 grid((unsigned)div_up((size_t)J + 1, 256), (unsigned)lv.regions[l]);
+        dim3 grid((unsigned)lv.regions[l], (unsigned)div_up((size_t)J + 1, 256));
         RSN_LAUNCH(k_parse_up, grid, 256, 0, s, pp.E0.as<uint16_t>(), pp.T[l - 1].as<uint16_t>(), pp.T[l].as<uint16_t>(), l,
                    lv.rsize[l - 1], lv.rsize[l], J, n);
     }
@@ -700,7 +700,7 @@ int lzss_escape_dev(const uint8_t *d_in, size_t n, uint8_t **d_out, size_t *out_
     RSN_TRY(lzss_escape(d_in, n, enc_buf, &enc, &en, s));
     RSN_TRY(out.alloc_out(en + 64, s));
     if (en) RSN_CUDA(cudaMemcpyAsync(out.p, enc, en, cudaMemcpyDeviceToDevice, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     *d_out = (uint8_t *)out.release();
     *out_n = en;
     return RSN_OK;
@@ -829,7 +829,7 @@ __global__ void kb_parse_up(LzBatch b) {  // grid: (rel chunks, level-1 regions,
     const size_t rsize1 = (size_t)kPB * kBatchFan;
     if ((size_t)blockIdx.y * rsize1 >= f.en) return;
     parse_up_body(b.E0 + (size_t)blockIdx.z * b.e0_stride, nullptr, b.T1 + (size_t)blockIdx.z * b.t1_stride, 1, kPB,
-                  rsize1, f.W, (size_t)f.en, blockIdx.y);
+                  rsize1, f.W, (size_t)f.en, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void kb_parse_top(LzBatch b, size_t G) {  // one thread per file
@@ -964,7 +964,7 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     HostVec<uint64_t> h_outn(G);
     if (!h_outn.data()) return RSN_ERR_NOMEM;
     RSN_CUDA(cudaMemcpyAsync(h_outn.data(), outn.p, G * 8, cudaMemcpyDeviceToHost, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
 
     // one result buffer for the group, files at 256-byte aligned offsets
     HostVec<uint8_t *> h_outp(G);
@@ -982,7 +982,7 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     }
     RSN_CUDA(cudaMemcpyAsync(outp.p, h_outp.data(), G * 8, cudaMemcpyHostToDevice, s));
     RSN_LAUNCH(kb_emit_write, dim3((unsigned)blocks_cap, g), kPT, 0, s, b, outp.as<uint8_t *>());
-    RSN_CUDA(cudaStreamSynchronize(s));  // h_outp is read by the copy above
+    RSN_CUDA(stream_wait(s));  // h_outp is read by the copy above
     out.owned.push_back(res.release());
     return RSN_OK;
 }
@@ -1063,7 +1063,7 @@ int shard_upload_escape(Sharded &sh, int g, DevBuf &d_in, DevBuf &enc_buf, cudaS
     const uint8_t *e = nullptr;
     size_t en = 0;
     RSN_TRY(lzss_escape(d_in.as<uint8_t>(), len, enc_buf, &e, &en, s));
-    RSN_CUDA(cudaStreamSynchronize(s));
+    RSN_CUDA(stream_wait(s));
     sh.enc[g] = e;
     sh.A[g + 1] = en;  // lengths for now; prefix-summed by shard 0
     return RSN_OK;
@@ -1085,7 +1085,7 @@ int shard_assemble(Sharded &sh, int g, size_t lo, size_t hi, DevBuf &slice, cuda
             sh.peer_bytes.fetch_add(y - x);
         }
     }
-    RSN_CUDA(cudaStreamSynchronize(s));  // the sources belong to other threads' arenas: done before the next barrier
+    RSN_CUDA(stream_wait(s));  // the sources belong to other threads' arenas: done before the next barrier
     return RSN_OK;
 }
 
@@ -1141,7 +1141,7 @@ void shard_thread(Sharded &sh, int g) {
         RSN_LAUNCH(k_shard_exits, (unsigned)div_up((size_t)J + 1, 256), 256, 0, s, pp.E0.as<uint16_t>(),
                    pp.T[pp.lv.top].as<uint16_t>(), pp.lv.top, pp.lv.rsize[pp.lv.top], J, n_own, dex.as<uint16_t>());
         RSN_CUDA(cudaMemcpyAsync(ex.data(), dex.p, ((size_t)J + 1) * 2, cudaMemcpyDeviceToHost, s));
-        RSN_CUDA(cudaStreamSynchronize(s));
+        RSN_CUDA(stream_wait(s));
         return RSN_OK;
     };
     if (sh.ok()) sh.fail(step3());
@@ -1173,11 +1173,11 @@ void shard_thread(Sharded &sh, int g) {
         RSN_TRY(d_out.alloc(sh.total[g] + 16, s));
         RSN_TRY(parse_emit(cfg, d_enc, d_lo, n_own, pp, d_out.as<uint8_t>(), s));
         RSN_CUDA(cudaMemcpyAsync(sh.h_out + sh.O[g], d_out.p, sh.total[g], cudaMemcpyDeviceToHost, s));
-        RSN_CUDA(cudaStreamSynchronize(s));
+        RSN_CUDA(stream_wait(s));
         return RSN_OK;
     };
     if (sh.ok()) sh.fail(step4());
-    if (s) cudaStreamSynchronize(s);
+    if (s) stream_wait(s);
     sh.bar.wait();  // nobody rewinds its arena while another shard may still read from it
 }
 

@@ -45,6 +45,9 @@ def check(sizes):
 def test_config4_shape_is_groups_of_256():
     groups = check([262144] * 4096)
     assert sorted(len(v) for v in groups.values()) == [256] * 16
+    # a rank's share when the batch is split over 8 GPUs: one group for each of 8 workers
+    groups = check([262144] * 512)
+    assert sorted(len(v) for v in groups.values()) == [64] * 8
 
 
 def test_mixed_sizes_do_not_share_a_group():
