@@ -103,6 +103,26 @@ int rsn_compress_layers(const char *algorithms, const uint8_t *in, size_t n, uin
 int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
 
 /*
+ * engine.BenchmarkFile (engine/engine.go:357-441) for one buffer: Shannon entropy (natural log) of
+ * the input bytes, compress + decompress through the layer list (the timed region), lossless flag,
+ * ratio in percent as float32, and ActualEntropy exactly as the reference computes it (histogram of
+ * the DEcompressed bytes over the COMPRESSED length, engine.go:412-423).  Histograms and the
+ * comparison run on the device.  A codec failure sets `failed` (and `error`) and returns RSN_OK, as
+ * AsyncBenchmarkFile's recover() turns a panic into a Failed row (engine.go:315-328).
+ */
+typedef struct rsn_bench_result {
+    double seconds;        /* compress + decompress, wall clock, host buffer in */
+    double entropy;        /* Result.Entropy */
+    float actual_entropy;  /* Result.ActualEntropy */
+    float ratio;           /* Result.Ratio */
+    int lossless;          /* Result.Lossless */
+    int failed;            /* Result.Failed */
+    int error;             /* the codec's code when failed */
+    size_t compressed_n, decompressed_n;
+} rsn_bench_result;
+int rsn_benchmark_file(const char *algorithms, const uint8_t *in, size_t n, rsn_bench_result *res);
+
+/*
  * Batches of independent files (BASELINE configs[3]; what engine.BenchmarkSuite's per-file loop does,
  * engine.go:208-262): file i is compressed (or decompressed) with the layer list exactly as
  * rsn_compress_layers would.  Host buffers (device == 0): files of up to 4 MiB are cut into groups
@@ -111,7 +131,9 @@ int rsn_decompress_layers(const char *algorithms, const uint8_t *in, size_t n, u
  * the files that go one by one (empty, larger than 4 MiB), are spread over `workers` host threads
  * (0 = default), each with its own CUDA stream.  out[i]/out_n[i] receive library-owned buffers
  * (rsn_free each); rcs[i] (optional) the per-file code: a file the reference would panic on fails
- * alone.  Returns RSN_OK or the first failing file's code.  With device != 0 the in/out pointers
+ * alone.  The per-file host work of a group (leaf order, header bytes) uses cores / workers helper
+ * threads; RSN_HOST_CORES in the environment overrides the core count (set it to cores / ranks when
+ * several ranks share a box).  Returns RSN_OK or the first failing file's code.  With device != 0 the in/out pointers
  * are device pointers on the calling thread's device: inputs are used in place (grouped like host
  * files when 16-byte aligned, otherwise one by one), every result is its own device buffer
  * (release with rsn_dev_free(p, NULL)); nothing crosses PCIe except sizes — and, when the first

@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, "libraisin_b200.so")
 EXPORTS = [
     "rsn_init", "rsn_shutdown", "rsn_strerror", "rsn_last_cuda_error", "rsn_free", "rsn_free_many", "rsn_dev_free_many", "rsn_host_alloc",
     "rsn_host_free", "rsn_lzss_compress", "rsn_lzss_compress_sharded", "rsn_sharded_peer_bytes", "rsn_lzss_decompress", "rsn_huff_compress", "rsn_huff_decompress",
-    "rsn_compress_layers", "rsn_decompress_layers", "rsn_batch_layers", "rsn_batch_plan", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
+    "rsn_compress_layers", "rsn_decompress_layers", "rsn_benchmark_file", "rsn_batch_layers", "rsn_batch_plan", "rsn_dev_lzss_compress", "rsn_dev_lzss_decompress",
     "rsn_dev_huff_compress", "rsn_dev_huff_decompress", "rsn_dev_free", "rsn_dev_download", "rsn_dev_upload",
     "rsn_dev_lzss_match", "rsn_dev_lzss_emit", "rsn_dev_lzss_escape",
     "rsn_kernel_launches", "rsn_reset_kernel_launches", "rsn_kernel_timing", "rsn_kernel_timing_report", "rsn_version",
@@ -31,6 +31,12 @@ class RaisinPanic(RuntimeError):
     def __init__(self, rc: int, msg: str):
         super().__init__(f"raisin_b200: {msg} (rc={rc})")
         self.rc = rc
+
+
+class BenchResult(C.Structure):
+    _fields_ = [("seconds", C.c_double), ("entropy", C.c_double), ("actual_entropy", C.c_float), ("ratio", C.c_float),
+                ("lossless", C.c_int), ("failed", C.c_int), ("error", C.c_int), ("compressed_n", C.c_size_t),
+                ("decompressed_n", C.c_size_t)]
 
 
 _lib = None
@@ -76,6 +82,8 @@ def lib():
     L.rsn_huff_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, u8pp, szp]
     L.rsn_compress_layers.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, u8pp, szp]
     L.rsn_decompress_layers.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, u8pp, szp]
+    L.rsn_benchmark_file.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(BenchResult)]
+    L.rsn_benchmark_file.restype = C.c_int
     L.rsn_batch_layers.argtypes = [C.c_char_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int]
     L.rsn_batch_layers.restype = C.c_int

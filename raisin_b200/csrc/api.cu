@@ -6,7 +6,9 @@
 #include "lzss.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -218,6 +220,114 @@ static int layers_host(const char *algorithms, bool compress, const uint8_t *in,
     size_t rn = 0;
     RSN_TRY(layers_dev(algos, compress, d.as<uint8_t>(), n, &r, &rn, s));
     return to_host(r, rn, out, out_n, s);
+}
+
+}  // extern "C"
+
+namespace rsn {
+namespace {
+// engine.BenchmarkFile's side computations (engine.go:367-377, 408, 412-423) on the device: byte
+// histogram (256 bins per CTA in shared memory, 16-byte loads, one flush per CTA) and the
+// DeepEqual of input and round trip.
+__global__ void __launch_bounds__(256) k_byte_hist(const uint8_t *__restrict__ in, size_t n,
+                                                   unsigned long long *__restrict__ hist) {
+    __shared__ uint32_t bins[256];
+    bins[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t per = (size_t)64 << 10;  // bytes per CTA
+    const size_t lo = (size_t)blockIdx.x * per, hi = min(n, lo + per);
+    for (size_t i = lo + (size_t)threadIdx.x * 16; i < hi; i += 256 * 16) {
+        uint8_t v[16];
+        load16(in, i, hi, 0, v);
+        const int valid = (int)min((size_t)16, hi - i);
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (k < valid) atomicAdd(&bins[v[k]], 1u);
+    }
+    __syncthreads();
+    if (bins[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)bins[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_bytes_differ(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
+                                                      size_t n, uint32_t *__restrict__ differ) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i >= n) return;
+    uint8_t x[16], y[16];
+    load16(a, i, n, 0, x);
+    load16(b, i, n, 0, y);
+    bool d = false;
+#pragma unroll
+    for (int k = 0; k < 16; k++) d |= x[k] != y[k];
+    if (d) *differ = 1;
+}
+// natural-log Shannon entropy of counts / total (goent.Entropy with math.Log)
+double entropy_nat(const unsigned long long *hist, double total) {
+    double e = 0;
+    for (int b = 0; b < 256; b++)
+        if (hist[b]) {
+            const double p = (double)hist[b] / total;
+            e -= p * log(p);
+        }
+    return e;
+}
+}  // namespace
+}  // namespace rsn
+
+extern "C" {
+
+// engine.BenchmarkFile (engine/engine.go:357-441) in one call: entropy of the input, compress and
+// decompress through the layer list (the timed region, wall clock, host buffer in), lossless flag,
+// ratio, and the "actual entropy" exactly as the reference computes it — the histogram of the
+// DEcompressed bytes divided by the COMPRESSED length (engine.go:412-418; the README's tables carry
+// those values).  A codec failure (the reference would panic and AsyncBenchmarkFile would report
+// Failed, engine.go:315-328) sets res->failed and returns RSN_OK.
+int rsn_benchmark_file(const char *algorithms, const uint8_t *in, size_t n, rsn_bench_result *res) {
+    if ((!in && n) || !res) return RSN_ERR_INVALID_ARG;
+    std::vector<Algo> algos;
+    RSN_TRY(parse_layers(algorithms, algos));
+    RSN_TRY(ensure_ctx());
+    cudaStream_t s = ctx().own_stream;
+    ArenaScope scope(s);
+    memset(res, 0, sizeof(*res));
+    timespec t0, t1;
+    DevBuf d, dh;
+    RSN_TRY(dh.alloc(2 * 256 * 8 + 16, s));
+    unsigned long long *h_in = dh.as<unsigned long long>(), *h_back = h_in + 256;
+    uint32_t *differ = reinterpret_cast<uint32_t *>(h_back + 256);
+    RSN_CUDA(cudaMemsetAsync(dh.p, 0, 2 * 256 * 8 + 16, s));
+    clock_gettime(CLOCK_MONOTONIC, &t0);  // start := time.Now() comes after the histogram in the reference;
+    RSN_TRY(to_device(in, n, d, s));      // the upload is this implementation's cost and is timed
+    if (n) RSN_LAUNCH(k_byte_hist, (unsigned)div_up(n, (size_t)64 << 10), 256, 0, s, d.as<uint8_t>(), n, h_in);
+    uint8_t *comp = nullptr, *back = nullptr;
+    size_t comp_n = 0, back_n = 0;
+    int rc = layers_dev(algos, true, d.as<uint8_t>(), n, &comp, &comp_n, s);
+    if (rc == RSN_OK) rc = layers_dev(algos, false, comp, comp_n, &back, &back_n, s);
+    if (rc == RSN_OK) RSN_CUDA(stream_wait(s));
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    HostVec<unsigned long long> hh(2 * 256 + 2);
+    if (!hh.data()) rc = rc == RSN_OK ? RSN_ERR_NOMEM : rc;
+    if (rc == RSN_OK) {
+        if (back_n) RSN_LAUNCH(k_byte_hist, (unsigned)div_up(back_n, (size_t)64 << 10), 256, 0, s, back, back_n, h_back);
+        if (back_n == n && n)
+            RSN_LAUNCH(k_bytes_differ, (unsigned)div_up(div_up(n, 16), 256), 256, 0, s, d.as<uint8_t>(), back, n, differ);
+        RSN_CUDA(cudaMemcpyAsync(hh.data(), dh.p, 2 * 256 * 8 + 16, cudaMemcpyDeviceToHost, s));
+        RSN_CUDA(stream_wait(s));
+    }
+    if (comp) out_free(comp, s);
+    if (back) out_free(back, s);
+    if (rc == RSN_ERR_CUDA || rc == RSN_ERR_NO_DEVICE || rc == RSN_ERR_NOMEM) return rc;
+    res->seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    if (rc != RSN_OK) {
+        res->failed = 1;
+        res->error = rc;
+        return RSN_OK;
+    }
+    res->compressed_n = comp_n;
+    res->decompressed_n = back_n;
+    res->entropy = n ? entropy_nat(hh.data(), (double)n) : 0.0;
+    res->actual_entropy = (float)(comp_n ? entropy_nat(hh.data() + 256, (double)comp_n) : 0.0);
+    res->ratio = (float)comp_n / (float)n * 100.0f;
+    res->lossless = back_n == n && (uint32_t)hh[512] == 0;
+    return RSN_OK;
 }
 
 int rsn_compress_layers(const char *algorithms, const uint8_t *in, size_t n, uint8_t **out, size_t *out_n) {
@@ -577,8 +687,14 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
     const size_t units = groups.size() + singles.size();
     if ((size_t)workers > units) workers = (int)(units ? units : 1);
     {
-        const int hw = (int)std::thread::hardware_concurrency();
-        set_batch_host_threads(std::max(2, (hw > 0 ? hw : 8) / workers));
+        // host cores this process may count on: all of them, unless RSN_HOST_CORES says otherwise (one
+        // rank per GPU on a shared box: cores / ranks)
+        int hw = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("RSN_HOST_CORES")) {
+            const int v = atoi(e);
+            if (v >= 1) hw = v;
+        }
+        set_batch_host_threads(std::max(1, (hw > 0 ? hw : 8) / workers));
     }
     std::atomic<size_t> next{0};
     std::atomic<int> first_err{RSN_OK};

@@ -145,6 +145,17 @@ def BenchmarkFile(algorithms, path_or_bytes, fused: bool = False) -> Result:
         with open(path_or_bytes, "rb") as fh:
             fileContents = fh.read()
     name = ",".join(algorithms)
+    if fused:  # everything, histograms and the lossless comparison included, in one C-ABI call on the device
+        import ctypes as C
+
+        r = _lib.BenchResult()
+        ptr, n, keep = _lib._as_ptr(fileContents)
+        _lib.check(_lib.lib().rsn_benchmark_file(name.encode(), ptr, n, C.byref(r)))
+        del keep
+        if r.failed:
+            return Result(name, "DNF", float("nan"), float("nan"), float("nan"), False, True)
+        return Result(name, f"{r.seconds * 1e3:.2f}ms", float(r.ratio), float(r.actual_entropy), float(r.entropy),
+                      bool(r.lossless), False, r.seconds)
     try:
         import numpy as np
 

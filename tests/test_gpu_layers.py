@@ -61,6 +61,32 @@ def test_benchmark_file(rsn):
     assert r.Failed                               # the reference panics -> "DNF" row
 
 
+def test_benchmark_file_on_device_matches_readme_tables(rsn):
+    """rsn_benchmark_file (engine.BenchmarkFile with the histograms and the lossless check on the
+    device) against the tables the reference's README prints for its two example files
+    (README.md:150-170: ratio, ACTUAL ENTROPY, THEORETICAL ENTROPY, LOSSLESS to two decimals), and
+    against the host-side mirror on larger inputs."""
+    readme = {  # (engine, file) -> (ratio %, actual entropy, theoretical entropy, lossless)
+        ("huffman", b"Hello world!\n"): (307.69, 1.08, 2.20, True),
+        ("huffman", b"abcabcabcabcabcabcabcabc\n"): (92.00, 1.24, 1.22, True),
+        ("lzss", b"Hello world!\n"): (100.00, 2.20, 2.20, True),
+    }
+    for (engine, data), (ratio, actual, theo, lossless) in readme.items():
+        r = rsn.engine.BenchmarkFile([engine], data, fused=True)
+        assert not r.Failed and r.Lossless == lossless
+        assert f"{r.Ratio:.2f}" == f"{ratio:.2f}"
+        assert f"{r.ActualEntropy:.2f}" == f"{actual:.2f}"
+        assert f"{r.Entropy:.2f}" == f"{theo:.2f}"
+    for data in (synth.mixed(300000, 8, segment=50000), synth.text(100001, 9), b"a<b>c<d" * 3, bytes(range(256)) * 33):
+        a = rsn.engine.BenchmarkFile(ALGOS, data, fused=True)
+        b = rsn.engine.BenchmarkFile(ALGOS, data, fused=False)
+        assert (a.Lossless, a.Failed) == (b.Lossless, b.Failed)
+        assert abs(a.Entropy - b.Entropy) < 1e-12
+        assert abs(a.ActualEntropy - b.ActualEntropy) < 1e-5   # float32 in the reference's Result
+        assert abs(a.Ratio - b.Ratio) < 1e-3
+    assert rsn.engine.BenchmarkFile(["huffman"], b"", fused=True).Failed
+
+
 def test_mixed_corpus_config3_shape(rsn, oracle):
     """BASELINE config 3 shape at a size the oracle finishes quickly."""
     data = synth.mixed(3 << 20, 3)
