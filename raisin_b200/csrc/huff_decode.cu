@@ -214,6 +214,69 @@ __global__ void k_hdec_write(DecParams p, size_t subs, const uint64_t *__restric
     if (trunc) *err = 1;  // data[i] with i == len(data) (huffman.go:145)
 }
 
+// ---- exact fallback for streams that do not self-synchronise (a complete fixed-length code whose
+// length does not divide the subsequence size never re-aligns: the fix-up above would move one
+// subsequence per round).  A code that starts before a subsequence boundary ends fewer than M =
+// (longest code) bits after it, so the true start of subsequence t is t*256 + o for some o < M.
+// Decode every subsequence from all M candidate starts (M x the decode work, only ever paid by such
+// streams), which gives its transfer function "entry offset -> entry offset of the next one";
+// compose the functions block by block, walk the blocks, and hand every subsequence its true start.
+constexpr int kXferBlock = 256;  // subsequences per composition block
+
+__global__ void k_hdec_xfer(DecParams p, size_t subs, uint32_t M, uint8_t *__restrict__ E) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= subs * M) return;
+    const size_t t = idx / M;
+    const uint32_t o = (uint32_t)(idx % M);
+    const uint64_t limit = min((uint64_t)(t + 1) * kSubBits, p.max);
+    const uint64_t s0 = (uint64_t)t * kSubBits + o;
+    uint64_t e = s0, bytes;
+    bool trunc;
+    if (s0 < limit) e = decode_span<false>(p, s0, limit, bytes, trunc, nullptr);
+    E[idx] = (uint8_t)(e >= limit ? min(e - limit, (uint64_t)M - 1) : 0);
+}
+// F[b][o]: entry offset after the block's subsequences when the block is entered at offset o
+__global__ void k_hdec_xfer_blocks(const uint8_t *__restrict__ E, size_t subs, uint32_t M, uint8_t *__restrict__ F) {
+    const uint32_t o = threadIdx.x;
+    if (o >= M) return;
+    const size_t lo = (size_t)blockIdx.x * kXferBlock, hi = min(subs, lo + kXferBlock);
+    uint32_t e = o;
+    for (size_t t = lo; t < hi; t++) e = E[t * M + e];
+    F[(size_t)blockIdx.x * M + o] = (uint8_t)e;
+}
+__global__ void k_hdec_xfer_spine(const uint8_t *__restrict__ F, size_t blocks, uint32_t M, uint8_t *__restrict__ ent) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t e = 0;  // bit 0 starts a code
+    for (size_t b = 0; b < blocks; b++) {
+        ent[b] = (uint8_t)e;
+        e = F[b * M + e];
+    }
+}
+__global__ void k_hdec_xfer_starts(const uint8_t *__restrict__ E, const uint8_t *__restrict__ ent, size_t subs,
+                                   uint32_t M, uint64_t *__restrict__ start) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t lo = b * kXferBlock;
+    if (lo >= subs) return;
+    const size_t hi = min(subs, lo + kXferBlock);
+    uint32_t e = ent[b];
+    for (size_t t = lo; t < hi; t++) {
+        start[t] = (uint64_t)t * kSubBits + e;
+        e = E[t * M + e];
+    }
+}
+__global__ void k_hdec_recount(DecParams p, size_t subs, const uint64_t *__restrict__ start, uint64_t *__restrict__ cnt) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= subs) return;
+    const uint64_t limit = min((uint64_t)(t + 1) * kSubBits, p.max);
+    uint64_t bytes = 0;
+    bool trunc;
+    if (start[t] < limit) decode_span<false>(p, start[t], limit, bytes, trunc, nullptr);
+    cnt[t] = bytes;
+}
+
+constexpr int kSyncBatch = 4;       // fix-up rounds per look at the flags
+constexpr int kSyncMaxRounds = 16;  // then the stream is taken not to synchronise
+
 int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int strict, uint8_t **d_out, size_t *out_n,
                         cudaStream_t s) {
     ArenaScope scope(s);
@@ -343,18 +406,53 @@ int huff_decompress_dev(const uint8_t *d_in, size_t n, const uint8_t *h_in, int 
     RSN_TRY(endB.alloc(subs * 8, s));
     RSN_TRY(cnt.alloc(subs * 8, s));
     RSN_TRY(off.alloc((subs + 1) * 8, s));
-    RSN_TRY(flag.alloc(16, s));
+    RSN_TRY(flag.alloc(32, s));
     const unsigned grid = (unsigned)div_up(subs, 128);
     RSN_LAUNCH(k_hdec_init, grid, 128, 0, s, p, subs, start.as<uint64_t>(), endA.as<uint64_t>(), cnt.as<uint64_t>());
     uint64_t *e_prev = endA.as<uint64_t>(), *e_next = endB.as<uint64_t>();
-    for (size_t iter = 0; iter <= subs; iter++) {
-        RSN_CUDA(cudaMemsetAsync(flag.p, 0, 8, s));
-        RSN_LAUNCH(k_hdec_sync, grid, 128, 0, s, p, subs, start.as<uint64_t>(), e_prev, e_next, cnt.as<uint64_t>(),
-                   flag.as<uint32_t>());
-        uint64_t changed = 0;
-        RSN_TRY(read_u64(flag.as<uint64_t>(), &changed, s));
-        std::swap(e_prev, e_next);
-        if (!(uint32_t)changed) break;
+    bool converged = false;
+    Ctx &cx = ctx();
+    for (int rounds = 0; !converged && rounds < kSyncMaxRounds; rounds += kSyncBatch) {
+        // a few fix-up rounds back to back, one look at their "changed" flags
+        RSN_CUDA(cudaMemsetAsync(flag.p, 0, 32, s));
+        for (int r = 0; r < kSyncBatch; r++) {
+            RSN_LAUNCH(k_hdec_sync, grid, 128, 0, s, p, subs, start.as<uint64_t>(), e_prev, e_next, cnt.as<uint64_t>(),
+                       flag.as<uint32_t>() + r);
+            std::swap(e_prev, e_next);
+        }
+        RSN_CUDA(cudaMemcpyAsync(cx.h_scalars, flag.p, 16, cudaMemcpyDeviceToHost, s));
+        RSN_CUDA(stream_wait(s));
+        converged = reinterpret_cast<const uint32_t *>(cx.h_scalars)[kSyncBatch - 1] == 0;
+    }
+    if (!converged) {  // exact fallback: transfer functions over the M candidate starts
+        uint32_t M = 1;
+        {
+            std::vector<std::pair<int32_t, uint32_t>> st{{tree.root, 0u}};
+            while (!st.empty()) {
+                auto [node, depth] = st.back();
+                st.pop_back();
+                const HuffNode &nd = tree.nodes[node];
+                if (nd.left < 0) {
+                    M = std::max(M, depth);
+                    continue;
+                }
+                st.push_back({nd.left, depth + 1});
+                st.push_back({nd.right, depth + 1});
+            }
+        }
+        if (M > 255) return RSN_ERR_UNSUPPORTED;
+        const size_t xb = div_up(subs, (size_t)kXferBlock);
+        DevBuf E, F, ent;
+        RSN_TRY(E.alloc(subs * M + 16, s));
+        RSN_TRY(F.alloc(xb * M + 16, s));
+        RSN_TRY(ent.alloc(xb + 16, s));
+        RSN_LAUNCH(k_hdec_xfer, (unsigned)div_up(subs * M, 128), 128, 0, s, p, subs, M, E.as<uint8_t>());
+        RSN_LAUNCH(k_hdec_xfer_blocks, (unsigned)xb, 256, 0, s, E.as<uint8_t>(), subs, M, F.as<uint8_t>());
+        RSN_LAUNCH(k_hdec_xfer_spine, 1, 32, 0, s, F.as<uint8_t>(), xb, M, ent.as<uint8_t>());
+        RSN_LAUNCH(k_hdec_xfer_starts, (unsigned)div_up(xb, 128), 128, 0, s, E.as<uint8_t>(), ent.as<uint8_t>(), subs, M,
+                   start.as<uint64_t>());
+        RSN_LAUNCH(k_hdec_recount, grid, 128, 0, s, p, subs, start.as<uint64_t>(), cnt.as<uint64_t>());
+        tr.mark("exact fallback");
     }
     tr.mark("init+sync");
     RSN_TRY(spine_scan_u64(cnt.as<uint64_t>(), off.as<uint64_t>(), off.as<uint64_t>() + subs, subs, s));
@@ -403,6 +501,7 @@ __global__ void kb_hdec_init(const HdecFile *__restrict__ files, uint64_t *__res
     cnt[f.sub_base + t] = bytes;
 }
 
+// changed[blockIdx.y] is set when a subsequence of that file moved in this round
 __global__ void kb_hdec_sync(const HdecFile *__restrict__ files, uint64_t *__restrict__ start,
                              const uint64_t *__restrict__ end_prev, uint64_t *__restrict__ end_next,
                              uint64_t *__restrict__ cnt, uint32_t *__restrict__ changed) {
@@ -427,7 +526,7 @@ __global__ void kb_hdec_sync(const HdecFile *__restrict__ files, uint64_t *__res
     start[g] = s1;
     end_next[g] = e;
     cnt[g] = bytes;
-    *changed = 1;
+    changed[blockIdx.y] = 1;
 }
 
 __global__ void __launch_bounds__(256) kb_hdec_finish(HdecFile *__restrict__ files, const uint64_t *__restrict__ cnt,
@@ -575,7 +674,7 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
     RSN_TRY(endB.alloc(subs_total * 8 + 8, s));
     RSN_TRY(cnt.alloc(subs_total * 8 + 8, s));
     RSN_TRY(off.alloc(subs_total * 8 + 8, s));
-    RSN_TRY(flag.alloc(16, s));
+    RSN_TRY(flag.alloc(G * 4 + 16, s));
     HostVec<TreeJob> jobs(G);
     if (!jobs.data()) return RSN_ERR_NOMEM;
     for (size_t f = 0; f < G; f++) {
@@ -609,15 +708,27 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         RSN_LAUNCH(kb_hdec_init, grid, 128, 0, s, files.as<HdecFile>(), start.as<uint64_t>(), endA.as<uint64_t>(),
                    cnt.as<uint64_t>());
         uint64_t *e_prev = endA.as<uint64_t>(), *e_next = endB.as<uint64_t>();
-        for (size_t iter = 0; iter <= subs_cap; iter++) {
-            RSN_CUDA(cudaMemsetAsync(flag.p, 0, 8, s));
-            RSN_LAUNCH(kb_hdec_sync, grid, 128, 0, s, files.as<HdecFile>(), start.as<uint64_t>(), e_prev, e_next,
-                       cnt.as<uint64_t>(), flag.as<uint32_t>());
-            uint64_t changed = 0;
-            RSN_TRY(read_u64(flag.as<uint64_t>(), &changed, s));
-            std::swap(e_prev, e_next);
-            if (!(uint32_t)changed) break;
+        // fix-up rounds in batches of kSyncBatch, one look per batch at the per-file flags of its last
+        // round; files still moving after kSyncMaxRounds do not synchronise and take the
+        // single-stream call, which has the exact fallback
+        HostVec<uint32_t> h_changed(G);
+        if (!h_changed.data()) return RSN_ERR_NOMEM;
+        bool moving = true;
+        for (int rounds = 0; moving && rounds < kSyncMaxRounds; rounds += kSyncBatch) {
+            for (int r = 0; r < kSyncBatch; r++) {
+                if (r == kSyncBatch - 1) RSN_CUDA(cudaMemsetAsync(flag.p, 0, G * 4, s));
+                RSN_LAUNCH(kb_hdec_sync, grid, 128, 0, s, files.as<HdecFile>(), start.as<uint64_t>(), e_prev, e_next,
+                           cnt.as<uint64_t>(), flag.as<uint32_t>());
+                std::swap(e_prev, e_next);
+            }
+            RSN_CUDA(cudaMemcpyAsync(h_changed.data(), flag.p, G * 4, cudaMemcpyDeviceToHost, s));
+            RSN_CUDA(stream_wait(s));
+            moving = false;
+            for (size_t f = 0; f < G; f++) moving |= h_changed[f] != 0;
         }
+        if (moving)
+            for (size_t f = 0; f < G; f++)
+                if (h_changed[f] && h[f].subs) plan[f].per_file = true;
         RSN_LAUNCH(kb_hdec_finish, (unsigned)G, 256, 0, s, files.as<HdecFile>(), cnt.as<uint64_t>(), off.as<uint64_t>());
     }
     RSN_CUDA(cudaMemcpyAsync(h.data(), files.p, G * sizeof(HdecFile), cudaMemcpyDeviceToHost, s));

@@ -152,6 +152,9 @@ def generate(kind: str, n: int, seed: int = 1) -> bytes:
         return mixed(n, seed)
     if kind == "repetitive":
         return repetitive(n, seed, motif=3000)
+    if kind == "uniform8":  # eight equiprobable symbols: 3-bit codes, a Huffman stream that never self-synchronises
+        return np.random.default_rng(seed).integers(0, 8, size=n, dtype=np.uint8).tobytes().translate(
+            bytes.maketrans(bytes(range(8)), b"abcdefgh"))
     raise ValueError(kind)
 
 

@@ -131,3 +131,20 @@ def test_no_state_between_calls(rsn):
     b = rsn.huffman.Compress(b"second one")
     assert rsn.huffman.Decompress(a) == b"first message"
     assert rsn.huffman.Decompress(b) == b"second one"
+
+
+def test_non_synchronising_stream(rsn, oracle):
+    """Eight equiprobable symbols give eight 3-bit codes: a decoder that starts inside a code never
+    re-aligns (256 is not a multiple of 3), so the speculative fix-up would move one subsequence per
+    round.  The decoder must notice after a bounded number of rounds and take the exact path
+    (transfer functions over the candidate starts); same bytes as the oracle, single call and batch."""
+    data = synth.generate("uniform8", 4 << 20, 77)
+    comp = rsn.huffman.Compress(data)
+    assert comp == oracle.huff_compress(data)
+    assert rsn.huffman.Decompress(comp) == oracle.huff_decompress(comp) == data
+    small = [synth.generate("uniform8", 100000 + 977 * k, 80 + k) for k in range(5)] + [synth.text(90000, 3)]
+    blobs = [oracle.huff_compress(x) for x in small]
+    assert rsn.engine.batch(blobs, ["huffman"], False, workers=2) == small
+    # sixteen symbols: 4-bit codes DO re-align with 256-bit subsequences (control case)
+    data16 = bytes(0x61 + (b & 15) for b in synth.random_bytes(1 << 20, 5))
+    assert rsn.huffman.Decompress(rsn.huffman.Compress(data16)) == data16
