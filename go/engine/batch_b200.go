@@ -74,9 +74,17 @@ func BatchLayers(algorithms []string, compress bool, files [][]byte) (outs [][]b
 	if compress {
 		flag = 1
 	}
-	C.rsn_batch_layers(calgos, flag, C.size_t(n), (**C.uint8_t)(unsafe.Pointer(&ins[0])), &ns[0],
+	const notReached = -1000 // no code of the library: the call failed before it came to this file
+	for i := range rcs {
+		rcs[i] = notReached
+	}
+	rc := C.rsn_batch_layers(calgos, flag, C.size_t(n), (**C.uint8_t)(unsafe.Pointer(&ins[0])), &ns[0],
 		(**C.uint8_t)(unsafe.Pointer(&res[0])), &resN[0], &rcs[0], 0, 0)
 	for i := 0; i < n; i++ {
+		if rcs[i] == notReached { // unknown layer name, no device, ...: every file fails with the call's code
+			errs[i] = errors.New("raisin_b200: " + C.GoString(C.rsn_strerror(rc)))
+			continue
+		}
 		if rcs[i] != 0 {
 			if errs[i] == nil {
 				errs[i] = errors.New("raisin_b200: " + C.GoString(C.rsn_strerror(rcs[i])))
@@ -90,4 +98,22 @@ func BatchLayers(algorithms []string, compress bool, files [][]byte) (outs [][]b
 		C.rsn_free(unsafe.Pointer(res[i]))
 	}
 	return
+}
+
+// BenchmarkFileB200 is engine.BenchmarkFile (engine.go:357-441) with the histograms, the entropies
+// and the lossless comparison computed on the device in the same call as the layers
+// (rsn_benchmark_file).  The fields are those of engine.Result.
+func BenchmarkFileB200(algorithms []string, fileContents []byte) (timeTaken float64, ratio float32, actualEntropy float32,
+	entropy float64, lossless bool, failed bool) {
+	calgos := C.CString(strings.Join(algorithms, ","))
+	defer C.free(unsafe.Pointer(calgos))
+	var r C.rsn_bench_result
+	var p *C.uint8_t
+	if len(fileContents) > 0 {
+		p = (*C.uint8_t)(unsafe.Pointer(&fileContents[0]))
+	}
+	if rc := C.rsn_benchmark_file(calgos, p, C.size_t(len(fileContents)), &r); rc != 0 {
+		panic("raisin_b200: " + C.GoString(C.rsn_strerror(rc)))
+	}
+	return float64(r.seconds), float32(r.ratio), float32(r.actual_entropy), float64(r.entropy), r.lossless != 0, r.failed != 0
 }

@@ -76,3 +76,16 @@ func Decompress(fileContents []byte, useProgressBar bool) []byte {
 	runtime.KeepAlive(fileContents)
 	return b200Take(rc, out, n)
 }
+
+// CompressAsyncSharded is CompressAsync for ONE large stream with the match search sharded by
+// position range over ngpus GPUs of the box (BASELINE configs[4]); the bytes are those of
+// CompressAsync.  Not part of the reference's package: an extra entry point for callers that hold
+// very large buffers.
+func CompressAsyncSharded(fileContents []byte, maxSearchBufferLength int, ngpus int) []byte {
+	var out *C.uint8_t
+	var n C.size_t
+	rc := C.rsn_lzss_compress_sharded(b200Ptr(fileContents), C.size_t(len(fileContents)),
+		C.int64_t(maxSearchBufferLength), C.RSN_LZSS_ASYNC, C.int(ngpus), &out, &n)
+	runtime.KeepAlive(fileContents)
+	return b200Take(rc, out, n)
+}

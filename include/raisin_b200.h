@@ -49,7 +49,10 @@ extern "C" {
 
 /* Select the CUDA device for the calling thread's context (default: current device / 0). */
 int rsn_init(int device);
-/* Release every cached device/pinned buffer of the calling thread's context. */
+/*
+ * Release the calling thread's streams, events and scratch memory, and drain the process-wide
+ * caches of free result buffers.  A thread that exits releases its own resources by itself.
+ */
 void rsn_shutdown(void);
 const char *rsn_strerror(int rc);
 /* Text of the last CUDA error seen by the calling thread ("" if none). */
@@ -171,7 +174,9 @@ int rsn_dev_upload(const void *h_src, size_t n, void *d_dst, void *stream);
 /*
  * Per-position match arrays of variant A over an already-escaped device buffer: for each i,
  * packed[i] = (len << 16) | off as computed by compressorWorker (lzss.go:166-184).
- * Exposed for parity tests and for the position-range sharded path.  window in [1, 65535].
+ * Exposed for parity tests and for the torch.distributed form of the position-range sharded path.
+ * window in [1, 32768]; d_enc must be 4-byte aligned (RSN_ERR_INVALID_ARG otherwise).  off is exact
+ * where a reference can be emitted (len >= 4; lzss.go:143 needs len >= 6) and unspecified below.
  */
 int rsn_dev_lzss_match(const uint8_t *d_enc, size_t n, int64_t window, uint32_t *d_packed, void *stream);
 
