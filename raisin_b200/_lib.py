@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libraisin_b200.so")
+SO_PATH = os.environ.get("RSN_LIB_PATH") or os.path.join(_HERE, "libraisin_b200.so")  # RSN_LIB_PATH: A/B runs of two builds
 
 # every symbol include/raisin_b200.h declares
 EXPORTS = [

@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace rsn {
@@ -18,6 +19,9 @@ struct BatchIO {
     std::vector<uint64_t> n;
     std::vector<int> rc;               // RSN_OK, or the error that took the file out of the batch
     std::vector<void *> owned;         // result buffers (out_alloc) backing ptr[]
+    // device ranges, each inside ONE allocation, in which the stage laid its results out back to back:
+    // what lets the caller fetch a group's results with one copy per range instead of one per file
+    std::vector<std::pair<const uint8_t *, size_t>> spans;
     size_t size() const { return ptr.size(); }
     void resize(size_t g) {
         ptr.assign(g, nullptr);
@@ -27,6 +31,7 @@ struct BatchIO {
     void release(cudaStream_t s) {
         for (void *p : owned) out_free(p, s);
         owned.clear();
+        spans.clear();
     }
 };
 

@@ -105,6 +105,9 @@ void set_thread_blocking_sync(bool on);
 // kernel stops every other host thread from launching anything for those 4 ms (that is how the
 // batch path ran its groups' Huffman tree kernels strictly one after another).
 void *host_out_alloc(size_t n);
+// `parts` (null entries skipped) point into `block` (from host_out_alloc): from now on each part is
+// released with rsn_free on its own and the block follows the last one; at least one part is required
+void host_out_adopt_parts(void *block, void *const *parts, size_t count);
 template <typename T>
 struct HostVec {
     T *p = nullptr;

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <cstdio>
 #include <cstdlib>
@@ -47,6 +48,22 @@ cudaError_t stream_wait(cudaStream_t s) {
     }
     cudaError_t e = cudaEventRecord(t_wait_ev, s);
     if (e != cudaSuccess) return e;
+    // Most waits of a batch stage are for kernels of 10-150 us; waking a sleeping thread costs about
+    // as much again (the single-group timeline showed 0.2-0.6 ms between dependent kernels).  Poll
+    // for a short while first, sleep only behind the long kernels (match search, Huffman trees).
+    static const long spin_us = [] {
+        const char *v = getenv("RSN_WAIT_SPIN_US");
+        return v ? atol(v) : 120L;
+    }();
+    if (spin_us > 0) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            e = cudaEventQuery(t_wait_ev);
+            if (e != cudaErrorNotReady) return e;
+            if (std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() >= spin_us)
+                break;
+        }
+    }
     return cudaEventSynchronize(t_wait_ev);
 }
 
@@ -296,8 +313,19 @@ struct OutCache {
         int device;
     };
     std::unordered_map<void *, Ent> live;
-    // (device, size class) -> free buffers: a buffer only ever goes back to a caller on its own device
-    std::unordered_map<uint64_t, std::vector<std::pair<void *, cudaStream_t>>> free_;
+    // (device, size class) -> free buffers: a buffer only ever goes back to a caller on its own device.
+    // A free buffer remembers the stream that used it last and an event recorded there when it was
+    // freed: the next user, if it runs on another stream, makes ITS STREAM wait for that event.  (The
+    // host used to wait for the whole other stream here — with eight group workers handing
+    // intermediate buffers to one another that stalled a worker behind another worker's queue of
+    // match-search kernels, and a batch pass took anything between 73 and 460 ms.)
+    struct Free {
+        void *first;
+        cudaStream_t second;
+        cudaEvent_t ev;
+    };
+    std::unordered_map<uint64_t, std::vector<Free>> free_;
+    std::unordered_map<int, std::vector<cudaEvent_t>> ev_pool;  // per device
     static uint64_t key(int device, size_t c) { return ((uint64_t)(uint32_t)device << 48) ^ (uint64_t)c; }
     size_t cached = 0;
     static constexpr size_t kMaxCached = (size_t)16 << 30;
@@ -313,19 +341,30 @@ struct OutCache {
         const int dev = g_ctx.device;
         void *p = nullptr;
         cudaStream_t last = nullptr;
+        cudaEvent_t ev = nullptr;
         {
             std::lock_guard<std::mutex> g(mu);
             auto it = free_.find(key(dev, c));
             if (it != free_.end() && !it->second.empty()) {
                 p = it->second.back().first;
                 last = it->second.back().second;
+                ev = it->second.back().ev;
                 it->second.pop_back();
                 cached -= c;
                 live[p] = Ent{c, s, dev};
             }
         }
         if (p) {
-            if (last && last != s) cudaStreamSynchronize(last);  // its previous user may still be reading it
+            if (last && last != s) {  // its previous user may still be reading it
+                if (!ev || cudaStreamWaitEvent(s, ev, 0) != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaStreamSynchronize(last);
+                }
+            }
+            if (ev) {
+                std::lock_guard<std::mutex> g(mu);
+                ev_pool[dev].push_back(ev);
+            }
             return p;
         }
         if (cudaMalloc(&p, c) != cudaSuccess) {
@@ -349,12 +388,29 @@ struct OutCache {
             if (it == live.end()) return;  // not ours
             c = it->second.cap;
             const int dev = it->second.device;
-            live.erase(it);
             if (cached + c <= kMaxCached) {
-                free_[key(dev, c)].push_back({p, s});
+                cudaEvent_t ev = nullptr;
+                if (s) {
+                    auto &pool = ev_pool[dev];
+                    if (!pool.empty()) {
+                        ev = pool.back();
+                        pool.pop_back();
+                    } else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+                        cudaGetLastError();
+                        ev = nullptr;
+                    }
+                    if (ev && cudaEventRecord(ev, s) != cudaSuccess) {
+                        cudaGetLastError();
+                        pool.push_back(ev);
+                        ev = nullptr;
+                    }
+                }
+                live.erase(it);
+                free_[key(dev, c)].push_back(Free{p, s, ev});
                 cached += c;
                 return;
             }
+            live.erase(it);
         }
         cudaStreamSynchronize(s);
         cudaFree(p);
@@ -362,8 +418,14 @@ struct OutCache {
     void drain() {
         std::lock_guard<std::mutex> g(mu);
         for (auto &kv : free_)
-            for (auto &e : kv.second) cudaFree(e.first);
+            for (auto &e : kv.second) {
+                cudaFree(e.first);
+                if (e.ev) cudaEventDestroy(e.ev);
+            }
         free_.clear();
+        for (auto &kv : ev_pool)
+            for (cudaEvent_t e : kv.second) cudaEventDestroy(e);
+        ev_pool.clear();
         cached = 0;
     }
     // A stream is about to be destroyed (its owner has synchronised it): cached buffers last used
@@ -559,11 +621,35 @@ struct PinnedPool {
         live[p] = c;
         return p;
     }
+    // Parts of one block handed out as separate results (the outputs of a batch group arrive with
+    // one device-to-host copy): every part is freed on its own, the block goes back to the pool with
+    // the last of them.
+    std::unordered_map<void *, void *> part_of;    // part -> block
+    std::unordered_map<void *, size_t> parts_left;  // block -> parts not yet freed
+    void adopt_parts(void *block, void *const *parts, size_t count) {
+        std::lock_guard<std::mutex> g(mu);
+        size_t k = 0;
+        for (size_t i = 0; i < count; i++)
+            if (parts[i]) {
+                part_of[parts[i]] = block;
+                k++;
+            }
+        parts_left[block] = k;
+    }
     void put(void *p) {
         if (!p) return;
         size_t c = 0;
         {
             std::lock_guard<std::mutex> g(mu);
+            auto pt = part_of.find(p);
+            if (pt != part_of.end()) {
+                void *block = pt->second;
+                part_of.erase(pt);
+                auto left = parts_left.find(block);
+                if (left != parts_left.end() && --left->second > 0) return;
+                if (left != parts_left.end()) parts_left.erase(left);
+                p = block;  // the last part: the block itself is released below
+            }
             auto it = live.find(p);
             if (it == live.end()) return;  // not ours
             c = it->second;
@@ -591,6 +677,7 @@ PinnedPool &pinned() {
 }  // namespace
 
 void *host_out_alloc(size_t n) { return pinned().get(n); }
+void host_out_adopt_parts(void *block, void *const *parts, size_t count) { pinned().adopt_parts(block, parts, count); }
 
 }  // namespace rsn
 
@@ -646,6 +733,9 @@ void rsn_free_many(void *const *ptrs, size_t count) {
 }
 void rsn_dev_free_many(void *const *d_ptrs, size_t count, void *stream) {
     cudaStream_t s = stream ? (cudaStream_t)stream : rsn::ctx().own_stream;
+    // a stream with nothing pending orders nothing: the buffers go back without an event each
+    if (count > 1 && cudaStreamQuery(s) == cudaSuccess) s = nullptr;
+    else cudaGetLastError();
     for (size_t i = 0; i < count; i++)
         if (d_ptrs[i]) rsn::out_free(d_ptrs[i], s);
 }

@@ -758,6 +758,7 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         out.ptr[f] = res.as<uint8_t>() + h[f].out_base;
         out.n[f] = h[f].total;
     }
+    out.spans.push_back({res.as<uint8_t>(), res.bytes});
     out.owned.push_back(res.release());
     // the few files the kernels do not take (single-leaf trees) go through the per-file call
     for (size_t f = 0; f < G; f++) {

@@ -446,6 +446,16 @@ struct HencBatch {
     size_t tc_stride;
 };
 
+// the per-file lists of runes >= 256 (each at its own stride) back to back: one device-to-host copy
+// for the group instead of one per file
+__global__ void __launch_bounds__(256) kb_big_gather(HencBatch b, const uint64_t *__restrict__ at,
+                                                     uint32_t *__restrict__ dst) {
+    const uint32_t n = b.files[blockIdx.y].big_n;
+    const uint32_t *src = b.big + (size_t)blockIdx.y * b.big_stride;
+    uint32_t *d = dst + at[blockIdx.y];
+    for (uint32_t i = blockIdx.x * 1024u + threadIdx.x; i < min(n, (blockIdx.x + 1) * 1024u); i += 256) d[i] = src[i];
+}
+
 __global__ void __launch_bounds__(kTileThreads) kb_rune_hist(HencBatch b) {
     __shared__ uint32_t bins[kHistCopies][kSmallBins];
     __shared__ uint32_t fffd_sm;
@@ -631,16 +641,26 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
     RSN_CUDA(stream_wait(s));
     tr.mark("hist");
     // the per-file lists of runes >= 256, back to back in one pinned buffer
-    std::vector<size_t> big_at(G + 1, 0);
-    for (size_t f = 0; f < G; f++) big_at[f + 1] = big_at[f] + h[f].big_n;
+    HostVec<uint64_t> big_at(G + 1);
+    if (!big_at.data()) return RSN_ERR_NOMEM;
+    uint32_t big_max = 0;
+    big_at[0] = 0;
+    for (size_t f = 0; f < G; f++) {
+        big_at[f + 1] = big_at[f] + h[f].big_n;
+        big_max = std::max(big_max, h[f].big_n);
+    }
     HostVec<uint32_t> h_big(big_at[G] + 1);
     if (!h_big.data()) return RSN_ERR_NOMEM;
-    for (size_t f = 0; f < G; f++) {
-        if (!h[f].big_n) continue;
-        RSN_CUDA(cudaMemcpyAsync(h_big.data() + big_at[f], b.big + f * b.big_stride, (size_t)h[f].big_n * 4,
-                                 cudaMemcpyDeviceToHost, s));
+    if (big_at[G]) {
+        DevBuf d_at, d_all;
+        RSN_TRY(d_at.alloc((G + 1) * 8, s));
+        RSN_TRY(d_all.alloc(big_at[G] * 4, s));
+        RSN_CUDA(cudaMemcpyAsync(d_at.p, big_at.data(), (G + 1) * 8, cudaMemcpyHostToDevice, s));
+        RSN_LAUNCH(kb_big_gather, dim3((unsigned)div_up(big_max, 1024), g), 256, 0, s, b, d_at.as<uint64_t>(),
+                   d_all.as<uint32_t>());
+        RSN_CUDA(cudaMemcpyAsync(h_big.data(), d_all.p, big_at[G] * 4, cudaMemcpyDeviceToHost, s));
+        RSN_CUDA(stream_wait(s));
     }
-    RSN_CUDA(stream_wait(s));
     tr.mark("big lists d2h");
     // ---- host: leaves in the reference's order and header bytes per file; trees and codes on the
     // device, one warp per file (huff_tree.cu)
@@ -765,6 +785,7 @@ int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
         out.ptr[f] = res.as<uint8_t>() + out_base[f];
         out.n[f] = out_total[f];
     }
+    out.spans.push_back({res.as<uint8_t>(), res.bytes});
     out.owned.push_back(res.release());
     // alphabets beyond the device tree builder: the single-stream call
     for (size_t f = 0; f < G; f++) {

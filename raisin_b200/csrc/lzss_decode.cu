@@ -867,6 +867,7 @@ int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
                 out.rc[f] = sub_out.rc[f - lo];
             }
             out.owned.insert(out.owned.end(), sub_out.owned.begin(), sub_out.owned.end());
+            out.spans.insert(out.spans.end(), sub_out.spans.begin(), sub_out.spans.end());
         }
         return RSN_OK;
     }
@@ -935,8 +936,12 @@ int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s) {
         out.ptr[f] = (h[f].unesc ? out2.as<uint8_t>() : sb.as<uint8_t>()) + h[f].gbase;
         out.n[f] = h[f].unesc ? h[f].un_n : h[f].sbn;
     }
+    out.spans.push_back({sb.as<uint8_t>(), sb.bytes});
     out.owned.push_back(sb.release());
-    if (out2.p) out.owned.push_back(out2.release());
+    if (out2.p) {
+        out.spans.push_back({out2.as<uint8_t>(), out2.bytes});
+        out.owned.push_back(out2.release());
+    }
     return RSN_OK;
 }
 

@@ -983,6 +983,7 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     RSN_CUDA(cudaMemcpyAsync(outp.p, h_outp.data(), G * 8, cudaMemcpyHostToDevice, s));
     RSN_LAUNCH(kb_emit_write, dim3((unsigned)blocks_cap, g), kPT, 0, s, b, outp.as<uint8_t *>());
     RSN_CUDA(stream_wait(s));  // h_outp is read by the copy above
+    out.spans.push_back({res.as<uint8_t>(), res.bytes});
     out.owned.push_back(res.release());
     return RSN_OK;
 }
