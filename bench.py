@@ -78,6 +78,7 @@ class ClockSampler:
         self.index = index
         self.interval_ms = interval_ms
         self.rows = []
+        self.first = 0
         self.proc = None
 
     def start(self):
@@ -94,6 +95,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """The timed region starts here: earlier samples are not reported."""
+        self.first = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -105,7 +110,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             if len(r) < 8:
                 continue
             try:
@@ -539,6 +544,13 @@ def run_batch(args, rank, local_rank, world):
     del comp_all, back_sample
 
     # ---- timed: device resident
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation, ~1 s) stalls CUDA
+    # calls of other processes' threads now and then, and with the start inside the timed region one
+    # run in three measured a step of 260-460 ms instead of 205-225.  It keeps sampling through the
+    # timed region; only the samples taken there are reported.
+    sampler = ClockSampler(local_rank, interval_ms=250)
+    if not os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.start()
     warm = max(args.warmup, 3)
     for _ in range(warm):
         dev_pass()
@@ -547,14 +559,15 @@ def run_batch(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank, interval_ms=500)
-    sampler.start()
+    sampler.mark()
     wall = []
     for a, b in ev:
         flush.fill_(1)  # L2 flush between timed iterations, outside the events
         torch.cuda.synchronize()
         a.record()
         t0 = time.perf_counter()
+        if os.environ.get("RSN_ALLOC_TRACE"):
+            print(f"[bench] timed step {len(wall)}", file=sys.stderr, flush=True)
         dev_pass()
         b.record()
         torch.cuda.synchronize()
@@ -646,7 +659,7 @@ def run_batch(args, rank, local_rank, world):
                                                                l2="flushed between timed iterations (256 MiB write)"),
             "timing": "CUDA events on the default stream around each step (the C-ABI calls return when the step's "
                       "work has finished), max over ranks; wall clock beside it",
-            "wall_ms_per_step": wall_ms,
+            "wall_ms_per_step": wall_ms, "step_ms": [round(a.elapsed_time(b), 1) for a, b in ev],
             "compressed_bytes": csum_all, "lzss_stage_bytes_rank0": c_lz, "lossless_files_rank0": lossless,
             "files_rank0": n,
             "e2e": {"value": total_all / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": total + hc,

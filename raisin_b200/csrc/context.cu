@@ -159,6 +159,28 @@ int ensure_ctx() {
     return init_ctx(-1);
 }
 
+// RSN_ALLOC_TRACE=1: one line on stderr for every allocation that had to go to the driver (arena
+// growth, result-buffer or pinned-pool miss) with the time it took: these are the calls that stall
+// every other thread of the process.
+static bool alloc_trace() {
+    static const bool on = [] {
+        const char *v = getenv("RSN_ALLOC_TRACE");
+        return v && v[0] == '1';
+    }();
+    return on;
+}
+struct AllocTimer {
+    const char *what;
+    size_t bytes;
+    std::chrono::steady_clock::time_point t0;
+    AllocTimer(const char *w, size_t n) : what(w), bytes(n), t0(std::chrono::steady_clock::now()) {}
+    ~AllocTimer() {
+        if (!alloc_trace()) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[rsn alloc] %-12s %10zu bytes %8.3f ms\n", what, bytes, ms);
+    }
+};
+
 // ----------------------------------------------------------------------------- arena
 
 namespace {
@@ -166,6 +188,14 @@ struct ArenaBlock {
     char *p;
     size_t cap, off;
 };
+// A call's temporaries are bump-allocated from blocks its thread holds for the duration of the
+// outermost ArenaScope.  The blocks themselves belong to the PROCESS: a scope takes them from a pool
+// (best fit) and hands them back when it ends, each with an event recorded on the scope's stream that
+// the next taker's stream waits for.  Blocks used to belong to threads, and a batch worker whose
+// share of a later pass was larger than anything it had seen before grew its arena in the middle of
+// the pass: a 1.8 GB cudaMalloc (50-120 ms), then cudaFree of the old chain (which waits for every
+// stream of the device) and a second cudaMalloc — one 4096-file pass in five took 270-2100 ms instead
+// of 205.  With the pool whichever worker draws the large group finds the large block.
 struct Arena {
     std::vector<ArenaBlock> blocks;
     size_t cur = 0;
@@ -176,8 +206,95 @@ struct Arena {
 thread_local Arena g_arena;
 
 constexpr size_t kArenaAlign = 256;
-constexpr size_t kArenaMinBlock = (size_t)64 << 20;
+constexpr size_t kArenaMinBlock = (size_t)128 << 20;
 
+struct ArenaPool {
+    std::mutex mu;
+    struct Ent {
+        char *p;
+        size_t cap;
+        int device;
+        cudaStream_t last;
+        cudaEvent_t ev;
+    };
+    std::vector<Ent> free_;
+    std::unordered_map<int, std::vector<cudaEvent_t>> evs;
+
+    // smallest free block of this device that holds `need` bytes; its previous user's work is
+    // ordered before anything the taker queues on `s`
+    bool take(int dev, size_t need, cudaStream_t s, ArenaBlock &out) {
+        Ent e{};
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].device == dev && free_[i].cap >= need && (best == free_.size() || free_[i].cap < free_[best].cap))
+                    best = i;
+            if (best == free_.size()) return false;
+            e = free_[best];
+            free_[best] = free_.back();
+            free_.pop_back();
+        }
+        if (e.ev) {
+            if (e.last != s && cudaStreamWaitEvent(s, e.ev, 0) != cudaSuccess) {
+                cudaGetLastError();
+                cudaEventSynchronize(e.ev);
+            }
+            std::lock_guard<std::mutex> g(mu);
+            evs[dev].push_back(e.ev);
+        }
+        out = ArenaBlock{e.p, e.cap, 0};
+        return true;
+    }
+    void give(int dev, const ArenaBlock &b, cudaStream_t s) {
+        cudaEvent_t ev = nullptr;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto &pool = evs[dev];
+            if (!pool.empty()) {
+                ev = pool.back();
+                pool.pop_back();
+            }
+        }
+        if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            ev = nullptr;
+        }
+        if (ev && cudaEventRecord(ev, s) != cudaSuccess) {
+            cudaGetLastError();
+            cudaEventDestroy(ev);
+            ev = nullptr;
+        }
+        if (!ev) cudaStreamSynchronize(s);  // no event: the block goes back only once its work is done
+        std::lock_guard<std::mutex> g(mu);
+        free_.push_back(Ent{b.p, b.cap, dev, s, ev});
+    }
+    void forget_stream(cudaStream_t s) {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &e : free_)
+            if (e.last == s) e.last = nullptr;
+    }
+    void drain() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &e : free_) {
+            if (e.ev) {
+                cudaEventSynchronize(e.ev);
+                cudaEventDestroy(e.ev);
+            }
+            cudaFree(e.p);
+        }
+        free_.clear();
+        for (auto &kv : evs)
+            for (cudaEvent_t e : kv.second) cudaEventDestroy(e);
+        evs.clear();
+    }
+};
+ArenaPool &arena_pool() {
+    static ArenaPool *p = new ArenaPool();  // leaked on purpose: safe at process exit
+    return *p;
+}
+
+// blocks a thread still holds (a scope that was never closed, or a thread that dies inside one)
 void arena_free_all() {
     for (auto &b : g_arena.blocks) cudaFree(b.p);
     g_arena.blocks.clear();
@@ -246,33 +363,34 @@ void *arena_alloc(size_t n) {
         }
         if (a.cur + 1 < a.blocks.size()) a.blocks[a.cur + 1].off = 0;
     }
-    size_t total = 0;
-    for (auto &b : a.blocks) total += b.cap;
-    size_t cap = n > total ? n : total;  // at least double the arena
-    if (cap < kArenaMinBlock) cap = kArenaMinBlock;
-    char *p = nullptr;
-    if (cudaMalloc((void **)&p, cap) != cudaSuccess) {
-        cudaGetLastError();
-        if (cap == n || cudaMalloc((void **)&p, n) != cudaSuccess) {
+    ArenaBlock nb{};
+    if (!arena_pool().take(g_ctx.device, n, a.last_stream, nb)) {
+        size_t cap = n + n / 4;  // some headroom: the same call on slightly larger data still fits
+        if (cap < kArenaMinBlock) cap = kArenaMinBlock;
+        char *p = nullptr;
+        AllocTimer at("arena", cap);
+        if (cudaMalloc((void **)&p, cap) != cudaSuccess) {
             cudaGetLastError();
-            return nullptr;
+            if (cap == n || cudaMalloc((void **)&p, n) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            cap = n;
         }
-        cap = n;
+        nb = ArenaBlock{p, cap, 0};
     }
-    a.blocks.push_back(ArenaBlock{p, cap, n});
+    nb.off = n;
+    a.blocks.push_back(nb);
     a.cur = a.blocks.size() - 1;
-    return p;
+    return nb.p;
 }
 
 ArenaScope::ArenaScope(cudaStream_t stream) : s(stream) {
     Arena &a = g_arena;
     if (a.depth == 0) {
-        // the arena's previous user may still have work in flight on another stream
-        if (a.used && a.last_stream != stream) cudaStreamSynchronize(a.last_stream);
         a.last_stream = stream;
         a.used = true;
         a.cur = 0;
-        if (!a.blocks.empty()) a.blocks[0].off = 0;
     }
     saved_block = a.cur;
     saved_off = a.blocks.empty() ? 0 : a.blocks[a.cur].off;
@@ -283,23 +401,15 @@ ArenaScope::~ArenaScope() {
     Arena &a = g_arena;
     a.depth--;
     if (a.depth > 0) {
+        // (a scope that opened on an empty arena saved block 0, offset 0: the start of the first block)
         a.cur = saved_block;
         if (!a.blocks.empty()) a.blocks[a.cur].off = saved_off;
         return;
     }
-    if (a.blocks.size() > 1) {
-        // the call outgrew the arena: replace the chain by one block so the next call fits in it
-        size_t total = 0;
-        for (auto &b : a.blocks) total += b.cap;
-        cudaStreamSynchronize(s);
-        arena_free_all();
-        char *p = nullptr;
-        total += total / 4;
-        if (cudaMalloc((void **)&p, total) == cudaSuccess) a.blocks.push_back(ArenaBlock{p, total, 0});
-        else cudaGetLastError();
-    }
+    // outermost scope: every block back to the pool, ordered behind this call's work
+    for (auto &b : a.blocks) arena_pool().give(g_ctx.device, b, s);
+    a.blocks.clear();
     a.cur = 0;
-    if (!a.blocks.empty()) a.blocks[0].off = 0;
 }
 
 // ----------------------------------------------------------------------------- result buffers
@@ -367,6 +477,7 @@ struct OutCache {
             }
             return p;
         }
+        AllocTimer at("result buf", c);
         if (cudaMalloc(&p, c) != cudaSuccess) {
             cudaGetLastError();
             drain();
@@ -445,7 +556,11 @@ OutCache &outs() {
 }
 }  // namespace
 
-void outs_forget_stream(cudaStream_t s) { outs().forget_stream(s); }
+void outs_forget_stream(cudaStream_t s) {
+    outs().forget_stream(s);
+    arena_pool().forget_stream(s);
+}
+void arena_drain() { arena_pool().drain(); }
 void *out_alloc(size_t n, cudaStream_t s) { return outs().get(n ? n : 1, s); }
 void out_free(void *p, cudaStream_t s) { outs().put(p, s); }
 
@@ -576,6 +691,38 @@ int spine_scan_u64(const uint64_t *d_in, uint64_t *d_out, uint64_t *d_total, siz
     return RSN_OK;
 }
 
+cudaError_t copy_many(void *const *dsts, const void *const *srcs, const size_t *sizes, size_t count, cudaStream_t s) {
+    std::vector<void *> d, sr;
+    std::vector<size_t> sz;
+    d.reserve(count);
+    sr.reserve(count);
+    sz.reserve(count);
+    for (size_t i = 0; i < count; i++)
+        if (sizes[i]) {
+            d.push_back(dsts[i]);
+            sr.push_back(const_cast<void *>(srcs[i]));
+            sz.push_back(sizes[i]);
+        }
+    if (d.empty()) return cudaSuccess;
+    static std::atomic<bool> batch_ok{true};
+    if (d.size() > 1 && batch_ok.load(std::memory_order_relaxed)) {
+        cudaMemcpyAttributes at{};
+        at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;  // the sources stay valid until the stream has passed the copies
+        at.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+        size_t first = 0, fail = 0;
+        const cudaError_t e = cudaMemcpyBatchAsync(d.data(), sr.data(), sz.data(), d.size(), &at, &first, 1, &fail, s);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();
+        if (e == cudaErrorNotSupported) batch_ok.store(false);  // older driver: one by one from now on
+        else if (e != cudaErrorInvalidValue) return e;           // (a kind of memory the batch call refuses: this batch one by one)
+    }
+    for (size_t i = 0; i < d.size(); i++) {
+        const cudaError_t e = cudaMemcpyAsync(d[i], sr[i], sz[i], cudaMemcpyDefault, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 int read_u64(const uint64_t *d_src, uint64_t *h_dst, cudaStream_t s) {
     Ctx &c = ctx();
     RSN_CUDA(cudaMemcpyAsync(c.h_scalars, d_src, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -613,6 +760,7 @@ struct PinnedPool {
             }
         }
         void *p = nullptr;
+        AllocTimer at("pinned", c);
         if (cudaHostAlloc(&p, c, cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();
             return nullptr;
@@ -694,6 +842,7 @@ void rsn_shutdown(void) {
     // a caller stay valid and are freed when they come back)
     rsn::pinned().drain();
     rsn::outs().drain();
+    rsn::arena_drain();
 }
 
 const char *rsn_strerror(int rc) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel timeline of one batch compress + decompress (library launch timer, RSN_KTIME_TIMELINE):
 how much of the wall time has 0, 1, 2+ kernels in flight, and which kernels run alone.
-usage: python tools/batch_timeline.py [files] [workers]"""
+usage: python tools/batch_timeline.py [files] [workers] [host]   (host: pinned host buffers in and out instead of device buffers)"""
 import ctypes as C
 import os
 import sys
@@ -14,6 +14,7 @@ import bench  # noqa: E402
 
 nfiles = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 workers = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+host_mode = len(sys.argv) > 3 and sys.argv[3] == "host"
 files = bench.make_files(list(range(nfiles)))
 import torch  # noqa: E402
 
@@ -25,6 +26,14 @@ n = len(files)
 ns = (C.c_size_t * n)(*[len(f) for f in files])
 d_blob = torch.frombuffer(bytearray(b"".join(files)), dtype=torch.uint8).cuda()
 ins = (C.c_void_p * n)(*[d_blob.data_ptr() + 262144 * i for i in range(n)])
+if host_mode:
+    h_ptrs = []
+    for f in files:
+        p = lib.rsn_host_alloc(len(f))
+        C.memmove(p, f, len(f))
+        h_ptrs.append(p)
+    ins = (C.c_void_p * n)(*h_ptrs)
+dev = 0 if host_mode else 1
 
 
 def one(timing):
@@ -32,21 +41,28 @@ def one(timing):
     if timing:
         lib.rsn_kernel_timing(1)
     t0 = time.perf_counter()
-    rsn._lib.check(lib.rsn_batch_layers(b"lzss,huffman", 1, n, ins, ns, outs, out_ns, rcs, workers, 1))
+    rsn._lib.check(lib.rsn_batch_layers(b"lzss,huffman", 1, n, ins, ns, outs, out_ns, rcs, workers, dev))
     t1 = time.perf_counter()
     b_outs, b_ns = (C.c_void_p * n)(), (C.c_size_t * n)()
-    rsn._lib.check(lib.rsn_batch_layers(b"lzss,huffman", 0, n, outs, out_ns, b_outs, b_ns, rcs, workers, 1))
+    rsn._lib.check(lib.rsn_batch_layers(b"lzss,huffman", 0, n, outs, out_ns, b_outs, b_ns, rcs, workers, dev))
     t2 = time.perf_counter()
     if timing:
         k = lib.rsn_kernel_timing_report(None, 0)
         lib.rsn_kernel_timing(0)
-    lib.rsn_dev_free_many(outs, n, None)
-    lib.rsn_dev_free_many(b_outs, n, None)
+    if host_mode:
+        lib.rsn_free_many(outs, n)
+        lib.rsn_free_many(b_outs, n)
+    else:
+        lib.rsn_dev_free_many(outs, n, None)
+        lib.rsn_dev_free_many(b_outs, n, None)
     return (t1 - t0) * 1e3, (t2 - t1) * 1e3
 
 
 for _ in range(3):
     one(False)
+if os.environ.get("TIMELINE_REPEAT"):  # spread of the untimed passes
+    for k in range(int(os.environ["TIMELINE_REPEAT"])):
+        print("pass %d: compress %.1f ms, decompress %.1f ms" % ((k,) + one(False)), flush=True)
 print("untimed: compress %.1f ms, decompress %.1f ms" % one(False))
 c, d = one(True)
 print("with launch timer: compress %.1f ms, decompress %.1f ms" % (c, d))
