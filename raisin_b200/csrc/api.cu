@@ -465,7 +465,9 @@ namespace {
 
 // One stage over a group, file by file (stages without a batched implementation, or groups the
 // batched one declines).
-int stage_per_file(Algo a, bool compress, const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s) {
+int stage_per_file(Algo a, bool compress, const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s,
+                   bool h_prefix_only = false) {
+    if (h_prefix_only) h_in = nullptr;  // the single-stream call wants the whole stream or none of it
     const size_t G = in.size();
     out.resize(G);
     out.rc = in.rc;
@@ -489,9 +491,11 @@ int stage_per_file(Algo a, bool compress, const BatchIO &in, const uint8_t *cons
     return RSN_OK;
 }
 
-int stage_batched(Algo a, bool compress, const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s) {
+int stage_batched(Algo a, bool compress, const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s,
+                  bool h_prefix_only = false) {
     if (a == ALGO_LZSS) return compress ? lzss_compress_batch(in, out, 4096, s) : lzss_decompress_batch(in, out, s);
-    if (a == ALGO_HUFFMAN) return compress ? huff_compress_batch(in, out, s) : huff_decompress_batch(in, h_in, out, s);
+    if (a == ALGO_HUFFMAN)
+        return compress ? huff_compress_batch(in, out, s) : huff_decompress_batch(in, h_in, out, s, h_prefix_only);
     return RSN_ERR_UNSUPPORTED;
 }
 
@@ -567,17 +571,57 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
             } else {
                 cur.ptr[f] = in[i];
                 h_in[f] = h_stage ? h_stage + off : nullptr;
-                if (h_stage) {
-                    dsts.push_back(h_stage + off);
-                    srcs.push_back(in[i]);
-                    sizes.push_back(in_n[i]);
-                }
             }
             off += (in_n[i] + 64 + 255) & ~(size_t)255;
         }
         RSN_CUDA(copy_many(dsts.data(), srcs.data(), sizes.data(), dsts.size(), s));
     }
-    if (h_stage) RSN_CUDA(stream_wait(s));
+    if (h_stage) {
+        // The header parser only reads a stream up to the byte after its first 5C 0A: fetch growing
+        // prefixes (4 KiB covers text-like alphabets, 64 KiB the ~2 800 records of a file of random
+        // bytes) instead of the whole stream — all of config 4's compressed files are 528 MB, their
+        // headers 35 MB, and nothing else runs while a pass waits for this copy.
+        std::vector<size_t> have(G, 0);
+        std::vector<char> done(G, 0);
+        const size_t rounds[3] = {(size_t)4 << 10, (size_t)64 << 10, ~(size_t)0};
+        for (int r = 0; r < 3; r++) {
+            std::vector<void *> dsts;
+            std::vector<const void *> srcs;
+            std::vector<size_t> sizes;
+            std::vector<size_t> upto(G, 0);
+            for (size_t f = 0; f < G; f++) {
+                const size_t n = in_n[idx[f]];
+                if (done[f]) continue;
+                upto[f] = std::min(n, rounds[r]);
+                dsts.push_back(const_cast<uint8_t *>(h_in[f]) + have[f]);
+                srcs.push_back(in[idx[f]] + have[f]);
+                sizes.push_back(upto[f] - have[f]);
+            }
+            if (dsts.empty()) break;
+            RSN_CUDA(copy_many(dsts.data(), srcs.data(), sizes.data(), dsts.size(), s));
+            RSN_CUDA(stream_wait(s));
+            for (size_t f = 0; f < G; f++) {
+                if (done[f]) continue;
+                const size_t n = in_n[idx[f]];
+                const uint8_t *h = h_in[f];
+                // first 5C 0A among the bytes present (rescan from one byte before the previous end)
+                size_t i = have[f] ? have[f] - 1 : 0;
+                bool found = false;
+                while (i + 1 < upto[f]) {
+                    const void *q = memchr(h + i, 0x5C, upto[f] - 1 - i);
+                    if (!q) break;
+                    i = (size_t)(static_cast<const uint8_t *>(q) - h);
+                    if (h[i + 1] == 0x0A) {
+                        found = true;
+                        break;
+                    }
+                    i++;
+                }
+                have[f] = upto[f];
+                if ((found && i + 3 <= have[f]) || have[f] == n) done[f] = 1;
+            }
+        }
+    }
     const bool have_host = !device || h_stage != nullptr;
     tr.mark(device ? "stage" : "h2d");
     const size_t k = algos.size();
@@ -585,10 +629,11 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
         const Algo a = compress ? algos[step] : algos[k - 1 - step];
         const uint8_t *const *hp = step == 0 && have_host ? h_in.data() : nullptr;  // host copies: first stage only
         BatchIO next;
-        int rc = stage_batched(a, compress, cur, hp, next, s);
+        const bool prefix_only = hp && h_stage != nullptr;
+        int rc = stage_batched(a, compress, cur, hp, next, s, prefix_only);
         if (rc == RSN_ERR_UNSUPPORTED) {
             next.release(s);
-            rc = stage_per_file(a, compress, cur, hp, next, s);
+            rc = stage_per_file(a, compress, cur, hp, next, s, prefix_only);
         }
         cur.release(s);
         if (rc != RSN_OK) {

@@ -41,8 +41,10 @@ constexpr size_t kBatchMaxFile = (size_t)4 << 20;
 int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStream_t s);
 int lzss_decompress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s);
 int huff_compress_batch(const BatchIO &in, BatchIO &out, cudaStream_t s);
-// h_in[f]: host copy of file f's stream (the header is parsed on the host)
-int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s);
+// h_in[f]: host copy of file f's stream (the header is parsed on the host); with `h_prefix_only` it
+// holds the stream up to and including the byte after the first 5C 0A (or all of it, if there is none)
+int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s,
+                          bool h_prefix_only = false);
 
 // host threads one group may use for its per-file host work (set per batch call from the core count
 // and the number of group workers)

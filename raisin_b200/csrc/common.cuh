@@ -16,6 +16,14 @@ struct Ctx {
     int device = -1;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // host->device chunks that overlap the first kernels
+    // Batches: the match search of a group (5 ms with every SM taken) runs on a stream of the lowest
+    // priority and everything else on the thread's own stream, which has the highest.  With one
+    // priority for all, the short kernels of a group that is past its match search queue behind the
+    // match searches of the other groups; the eight groups of a pass then move in lockstep, reach the
+    // host part of the Huffman stage together and leave the GPU idle for 8 ms and nearly idle for the
+    // 8 ms of their tree kernels, twice per pass.
+    cudaStream_t low_stream = nullptr;
+    cudaEvent_t low_before = nullptr, low_after = nullptr;
     cudaEvent_t chunk_ev[64] = {nullptr};
     bool ready = false;
     uint64_t launches = 0;

@@ -138,7 +138,14 @@ static int init_ctx(int device) {
     if (c.ready) release_thread_resources();  // streams, events and arena blocks belong to the old device
     RSN_CUDA(cudaSetDevice(device));
     c.device = device;
-    if (!c.own_stream) RSN_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    if (!c.own_stream) {
+        int least = 0, greatest = 0;
+        RSN_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        RSN_CUDA(cudaStreamCreateWithPriority(&c.own_stream, cudaStreamNonBlocking, greatest));
+        if (!c.low_stream) RSN_CUDA(cudaStreamCreateWithPriority(&c.low_stream, cudaStreamNonBlocking, least));
+        if (!c.low_before) RSN_CUDA(cudaEventCreateWithFlags(&c.low_before, cudaEventDisableTiming));
+        if (!c.low_after) RSN_CUDA(cudaEventCreateWithFlags(&c.low_after, cudaEventDisableTiming));
+    }
     if (!c.copy_stream) RSN_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     for (auto &e : c.chunk_ev)
         if (!e) RSN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -327,6 +334,14 @@ static void release_thread_resources() {
         cudaStreamDestroy(c.copy_stream);
         c.copy_stream = nullptr;
     }
+    if (c.low_stream) {
+        cudaStreamSynchronize(c.low_stream);
+        cudaStreamDestroy(c.low_stream);
+        c.low_stream = nullptr;
+    }
+    if (c.low_before) cudaEventDestroy(c.low_before);
+    if (c.low_after) cudaEventDestroy(c.low_after);
+    c.low_before = c.low_after = nullptr;
     for (auto &e : c.chunk_ev)
         if (e) {
             cudaEventDestroy(e);

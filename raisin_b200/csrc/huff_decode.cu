@@ -611,7 +611,8 @@ void hdec_host_plan(const uint8_t *h, size_t n, HdecHost &pl) {
 }
 }  // namespace
 
-int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s) {
+int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO &out, cudaStream_t s,
+                          bool h_prefix_only) {
     const size_t G = in.size();
     out.resize(G);
     out.rc = in.rc;
@@ -765,7 +766,7 @@ int huff_decompress_batch(const BatchIO &in, const uint8_t *const *h_in, BatchIO
         if (out.rc[f] != RSN_OK || !plan[f].per_file) continue;
         uint8_t *r = nullptr;
         size_t rn = 0;
-        out.rc[f] = huff_decompress_dev(in.ptr[f], (size_t)in.n[f], h_in[f], 0, &r, &rn, s);
+        out.rc[f] = huff_decompress_dev(in.ptr[f], (size_t)in.n[f], h_prefix_only ? nullptr : h_in[f], 0, &r, &rn, s);
         if (out.rc[f] != RSN_OK) continue;
         out.ptr[f] = r;
         out.n[f] = rn;

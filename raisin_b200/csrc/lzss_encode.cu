@@ -953,7 +953,23 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
     RSN_LAUNCH(kb_escape_count, dim3((unsigned)tiles_cap, g), kTileThreads, 0, s, b);
     RSN_LAUNCH(kb_escape_finish, g, 256, 0, s, b);
     RSN_LAUNCH(kb_escape_apply, dim3((unsigned)tiles_cap, g), kTileThreads, 0, s, b);
-    RSN_TRY(lzss_match_tile_batch(b.files, G, ecap, b.window, b.packed, b.packed_stride, s));
+    {
+        // the match search on the low-priority stream (see Ctx::low_stream), between two events
+        Ctx &c = ctx();
+        static const bool split = [] {
+            const char *v = getenv("RSN_K2_LOW_PRIORITY");
+            return !(v && v[0] == '0');
+        }();
+        if (split && c.low_stream && s == c.own_stream) {
+            RSN_CUDA(cudaEventRecord(c.low_before, s));
+            RSN_CUDA(cudaStreamWaitEvent(c.low_stream, c.low_before, 0));
+            RSN_TRY(lzss_match_tile_batch(b.files, G, ecap, b.window, b.packed, b.packed_stride, c.low_stream));
+            RSN_CUDA(cudaEventRecord(c.low_after, c.low_stream));
+            RSN_CUDA(cudaStreamWaitEvent(s, c.low_after, 0));
+        } else {
+            RSN_TRY(lzss_match_tile_batch(b.files, G, ecap, b.window, b.packed, b.packed_stride, s));
+        }
+    }
     RSN_LAUNCH(kb_parse_exits, dim3((unsigned)blocks_cap, g), kPT, 0, s, b);
     if (b.top)
         RSN_LAUNCH(kb_parse_up, dim3((unsigned)div_up((size_t)window + 1, 256), (unsigned)regions1, g), 256, 0, s, b);
