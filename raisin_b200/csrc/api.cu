@@ -695,7 +695,22 @@ int batch_group(const std::vector<Algo> &algos, bool compress, const std::vector
         if (members < 2 || (size_t)(hi - lo) > sum + sum / 4 + (members << 9)) continue;  // sparse: file by file
         uint8_t *block = (uint8_t *)host_out_alloc((size_t)(hi - lo));
         if (!block) continue;
-        cudaError_t e = cudaMemcpyAsync(block, lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, s);
+        // in pieces of 2 MiB, queued with one call: the copy engine takes copies in order, and the
+        // 8-byte size and flag read-backs of the OTHER workers' kernels would otherwise wait behind
+        // whole 64 MiB results (the last group of a pass crawled through 22 + 9 ms of such waits)
+        cudaError_t e;
+        {
+            const size_t piece = (size_t)2 << 20, span_n = (size_t)(hi - lo);
+            std::vector<void *> dsts;
+            std::vector<const void *> srcs;
+            std::vector<size_t> sizes;
+            for (size_t at = 0; at < span_n; at += piece) {
+                dsts.push_back(block + at);
+                srcs.push_back(lo + at);
+                sizes.push_back(std::min(piece, span_n - at));
+            }
+            e = copy_many(dsts.data(), srcs.data(), sizes.data(), dsts.size(), s);
+        }
         if (e != cudaSuccess) {
             rsn_free(block);
             rc = cuda_fail(e, "batch d2h", __FILE__, __LINE__);
@@ -804,7 +819,11 @@ int rsn_batch_layers(const char *algorithms, int compress, size_t count, const u
             note(RSN_ERR_CUDA);
             return;
         }
-        cudaStream_t s = ctx().own_stream;
+        static const bool stagger = [] {
+            const char *v = getenv("RSN_BATCH_STAGGER");
+            return !(v && v[0] == '0');
+        }();
+        cudaStream_t s = stagger && ctx().batch_stream ? ctx().batch_stream : ctx().own_stream;
         set_thread_blocking_sync(true);
         for (;;) {
             const size_t u = next.fetch_add(1);

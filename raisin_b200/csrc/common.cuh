@@ -24,6 +24,12 @@ struct Ctx {
     // 8 ms of their tree kernels, twice per pass.
     cudaStream_t low_stream = nullptr;
     cudaEvent_t low_before = nullptr, low_after = nullptr;
+    // The stream a batch worker runs its groups on.  Workers get DIFFERENT priorities (all above
+    // low_stream's): with equal priorities the GPU shares itself out evenly, the groups of a pass
+    // advance in lockstep and so do their copies — every worker uploads at the start and downloads at
+    // the end, with nothing running beside the copies.  Staggered, the first worker's group finishes
+    // first and its download runs under the other groups' kernels.
+    cudaStream_t batch_stream = nullptr;
     cudaEvent_t chunk_ev[64] = {nullptr};
     bool ready = false;
     uint64_t launches = 0;

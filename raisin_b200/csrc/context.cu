@@ -143,6 +143,13 @@ static int init_ctx(int device) {
         RSN_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         RSN_CUDA(cudaStreamCreateWithPriority(&c.own_stream, cudaStreamNonBlocking, greatest));
         if (!c.low_stream) RSN_CUDA(cudaStreamCreateWithPriority(&c.low_stream, cudaStreamNonBlocking, least));
+        if (!c.batch_stream) {
+            static std::atomic<int> ordinal{0};
+            const int levels = least - greatest;  // priorities greatest .. least-1 (least is the match search's)
+            const int k = ordinal.fetch_add(1);
+            const int prio = levels > 0 ? greatest + (k % levels) : greatest;
+            RSN_CUDA(cudaStreamCreateWithPriority(&c.batch_stream, cudaStreamNonBlocking, prio));
+        }
         if (!c.low_before) RSN_CUDA(cudaEventCreateWithFlags(&c.low_before, cudaEventDisableTiming));
         if (!c.low_after) RSN_CUDA(cudaEventCreateWithFlags(&c.low_after, cudaEventDisableTiming));
     }
@@ -338,6 +345,12 @@ static void release_thread_resources() {
         cudaStreamSynchronize(c.low_stream);
         cudaStreamDestroy(c.low_stream);
         c.low_stream = nullptr;
+    }
+    if (c.batch_stream) {
+        cudaStreamSynchronize(c.batch_stream);
+        outs_forget_stream(c.batch_stream);
+        cudaStreamDestroy(c.batch_stream);
+        c.batch_stream = nullptr;
     }
     if (c.low_before) cudaEventDestroy(c.low_before);
     if (c.low_after) cudaEventDestroy(c.low_after);

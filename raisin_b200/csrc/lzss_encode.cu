@@ -960,7 +960,7 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
             const char *v = getenv("RSN_K2_LOW_PRIORITY");
             return !(v && v[0] == '0');
         }();
-        if (split && c.low_stream && s == c.own_stream) {
+        if (split && c.low_stream && (s == c.own_stream || s == c.batch_stream)) {
             RSN_CUDA(cudaEventRecord(c.low_before, s));
             RSN_CUDA(cudaStreamWaitEvent(c.low_stream, c.low_before, 0));
             RSN_TRY(lzss_match_tile_batch(b.files, G, ecap, b.window, b.packed, b.packed_stride, c.low_stream));
