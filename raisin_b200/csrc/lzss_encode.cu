@@ -126,11 +126,11 @@ int lzss_escape(const uint8_t *d_in, size_t n, DevBuf &enc, const uint8_t **enc_
 // iterative variant (lzss.go:240-296) visits p, then p + 1 (no match may start at p) or
 // p + max(L,1) + 1 (the byte that ends a match is always a literal).  Either way the visited set
 // is the orbit of 0 under a per-position jump that only looks forward by at most J bytes.
-//   k_parse_exits   per 4096-position block, pointer doubling in shared memory: for EVERY position
+//   k_parse_exits   per 4096-position block, one warp, a right-to-left recurrence: for EVERY position
 //                   of the block, the first orbit position at or beyond the block end (u16, relative)
 //   k_parse_up/top/down   a 64-ary hierarchy of such exit tables gives every block's true entry
-//   k_emit_plan     per block: synchronous doubling again, this time scattering a "visited" mark
-//                   from the block's entry (after round r the first 2^(r+1) orbit points are marked);
+//   k_emit_plan     per block, one warp: the orbit from the block's entry, threaded through 32
+//                   sub-ranges whose speculative orbits were walked in parallel (see emit_plan_warp);
 //                   stores the visited bitmap and the block's output size
 //   k_emit_write    per block: token sizes -> block scan -> tokens staged in shared memory ->
 //                   coalesced copy to the output
@@ -185,62 +185,6 @@ __device__ __forceinline__ void load_jumps(const ParseCfg &cfg, const uint32_t *
     uint4 *dst = reinterpret_cast<uint4 *>(jump + p0);  // jump[] is 16-byte aligned, p0 a multiple of 16
     dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
-
-__device__ __forceinline__ void parse_exits_body(const ParseCfg &cfg, const uint32_t *__restrict__ lo, size_t n,
-                                                 uint16_t *__restrict__ E0) {
-    __shared__ __align__(16) uint16_t y[kPB];
-    const size_t start = (size_t)blockIdx.x * kPB;
-    const uint32_t nrel = (uint32_t)min((size_t)kPB, n - start);
-    load_jumps(cfg, lo, start, n, y);
-    __syncthreads();
-    const uint32_t p0 = threadIdx.x * kPI;
-    // from here on a thread owns the interleaved elements k*kPT + tid (conflict-free shared access)
-#pragma unroll
-    for (int k = 0; k < kPI; k++) {
-        const uint32_t p = k * kPT + threadIdx.x;
-        y[p] = (uint16_t)(p + y[p]);
-    }
-    __syncthreads();
-    // in-place pointer doubling: y[p] always names a later orbit point of p; racing reads see either
-    // the old or the new value of another element, both valid
-    for (;;) {
-        bool changed = false;
-#pragma unroll
-        for (int k = 0; k < kPI; k++) {
-            const uint32_t p = k * kPT + threadIdx.x;
-            const uint32_t v = y[p];
-            if (v < nrel) {
-                y[p] = y[v];
-                changed = true;
-            }
-        }
-        if (!__syncthreads_or(changed)) break;
-    }
-    uint32_t out[kPI];
-    {
-        const uint4 a = reinterpret_cast<const uint4 *>(y + p0)[0], b = reinterpret_cast<const uint4 *>(y + p0)[1];
-        const uint32_t yw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int k = 0; k < kPI; k++) {
-            const uint32_t v = (yw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-            out[k] = v >= (uint32_t)kPB ? v - kPB : 0u;  // 0: the orbit left the input inside this block
-        }
-    }
-    if (p0 + kPI <= nrel) {
-        uint4 *dst = reinterpret_cast<uint4 *>(E0 + start + p0);
-        dst[0] = make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16),
-                            out[6] | (out[7] << 16));
-        dst[1] = make_uint4(out[8] | (out[9] << 16), out[10] | (out[11] << 16), out[12] | (out[13] << 16),
-                            out[14] | (out[15] << 16));
-    } else {
-        for (int k = 0; k < kPI; k++)
-            if (p0 + k < nrel) E0[start + p0 + k] = (uint16_t)out[k];
-    }
-}
-__global__ void __launch_bounds__(kPT) k_parse_exits(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
-                                                     uint16_t *__restrict__ E0) {
-    parse_exits_body(cfg, lo, n, E0);
 }
 
 struct ParseLevels {
@@ -405,73 +349,221 @@ __device__ __forceinline__ uint8_t *put_dec64(uint8_t *o, uint64_t v) {
     return o + d;
 }
 
-// visited bitmap (one u16 per 16 positions) and output bytes of every block
-__device__ __forceinline__ void emit_plan_body(const ParseCfg &cfg, const uint32_t *__restrict__ lo, size_t n,
-                                               const uint64_t *__restrict__ entry0, uint16_t *__restrict__ visited,
-                                               uint64_t *__restrict__ blk_bytes) {
-    __shared__ __align__(16) uint16_t ya[kPB], yb[kPB];
-    __shared__ __align__(16) uint8_t mark[kPB];
-    __shared__ uint32_t sm[33];
-    const size_t start = (size_t)blockIdx.x * kPB;
+// visited bitmap (one u16 per 16 positions) and output bytes of every block.
+//
+// One WARP per block.  The orbit of the block's entry under p -> p + jump(p) is a chain of up to 4096
+// dependent steps; two orbits that start a few bytes apart merge after a step or two (both take the
+// same matches), which is what makes it parallel: every lane first walks the orbit of the START of
+// its 128-position sub-range and records it as a bit mask; then the true orbit is threaded through
+// the sub-ranges in order, each lane walking from the point where the true orbit enters its
+// sub-range only until it meets its speculative orbit (from there on the two are the same).  About
+// 37 + 3 steps per lane instead of 12 rounds of pointer doubling over all 4096 positions by 256
+// threads (a sixth of the instructions).
+constexpr int kPlanWarps = 4;                       // blocks per CTA
+constexpr int kPlanSub = kPB / 32;                  // 128 positions per lane
+constexpr int kPlanPitch = kPB + 2 * 32;            // one padding word per sub-range: lanes at the same
+                                                    // offset of their sub-ranges hit different banks
+__device__ __forceinline__ uint32_t plan_idx(uint32_t p) { return p + ((p / kPlanSub) << 1); }
+
+// jump[] of one block for one warp (swizzled by plan_idx); positions >= n get 1
+__device__ __forceinline__ void plan_load_jumps(const ParseCfg &cfg, const uint32_t *__restrict__ lo, size_t n,
+                                                size_t start, uint16_t *jump) {
+    const unsigned lane = threadIdx.x & 31;
+    // ---- jumps of the block's positions (positions >= n: 1), 4 positions per lane and turn; eight
+    // loads in flight per lane (one load per turn left the warp waiting for memory 32 times)
+    constexpr int kTurns = kPB / 128, kBatch = 8;
+    for (uint32_t it0 = 0; it0 < kTurns; it0 += kBatch) {
+      uint4 vv[kBatch];
+      const bool whole = start + (size_t)(it0 + kBatch) * 128 <= n;
+      if (whole) {
+#pragma unroll
+          for (int q = 0; q < kBatch; q++)
+              vv[q] = __ldg(reinterpret_cast<const uint4 *>(lo + start + (it0 + q) * 128 + lane * 4));
+      }
+#pragma unroll
+      for (int q = 0; q < kBatch; q++) {
+        const uint32_t it = it0 + q;
+        const uint32_t p = it * 128 + lane * 4;
+        uint32_t L[4];
+        if (whole) {
+            L[0] = vv[q].x >> 16;
+            L[1] = vv[q].y >> 16;
+            L[2] = vv[q].z >> 16;
+            L[3] = vv[q].w >> 16;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) L[k] = start + p + k < n ? (__ldg(lo + start + p + k) >> 16) : 0u;
+        }
+        uint32_t sb = 0;
+        if (cfg.variant == RSN_LZSS_ITER && start + p < n)  // 4 consecutive S bits (start + p is a multiple of 4)
+            sb = (__ldg(cfg.sbits + ((start + p) >> 5)) >> ((start + p) & 31)) & 0xFu;
+        uint32_t j[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            j[k] = L[k] ? L[k] : 1u;
+            if (cfg.variant == RSN_LZSS_ITER) j[k] = ((sb >> k) & 1u) ? j[k] + 1 : 1u;
+        }
+        uint32_t *dst = reinterpret_cast<uint32_t *>(jump + plan_idx(p));  // even u16 index: 4-byte aligned
+        dst[0] = j[0] | (j[1] << 16);
+        dst[1] = j[2] | (j[3] << 16);
+      }
+    }
+    __syncwarp();
+}
+
+// E0[p] for every position p of one block (one warp): the first orbit position at or beyond the block
+// end, relative to it (0: the orbit leaves the input inside the block).  exit(p) = exit(p + jump(p)) is a
+// recurrence from the right: every lane resolves its 128-position sub-range from its last position
+// down (a pointer either leaves the sub-range or lands on an entry that is already resolved), then
+// the sub-ranges are stitched from the last to the first, 128 positions at a time.  One pass over
+// the positions instead of ~12 rounds of pointer doubling over all of them.
+__device__ __forceinline__ void parse_exits_warp(const ParseCfg &cfg, const uint32_t *__restrict__ lo, size_t n,
+                                                 size_t block, uint16_t *__restrict__ E0, uint16_t *jump) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t start = block * kPB;
     const uint32_t nrel = (uint32_t)min((size_t)kPB, n - start);
-    const uint32_t p0 = threadIdx.x * kPI;
-    load_jumps(cfg, lo, start, n, ya);
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kPI; k++) {  // interleaved ownership: conflict-free shared access
-        const uint32_t p = k * kPT + threadIdx.x;
-        ya[p] = (uint16_t)(p + ya[p]);
-        mark[p] = 0;
+    plan_load_jumps(cfg, lo, n, start, jump);
+    __syncwarp();
+    const uint32_t sub0 = lane * kPlanSub, sub1 = min(sub0 + kPlanSub, nrel);
+    // in place: entries above p hold exits from the sub-range, entries up to p still hold jumps
+    for (uint32_t p = sub1; p-- > sub0;) {
+        uint32_t t = p + jump[plan_idx(p)];
+        if (t < sub1) t = jump[plan_idx(t)];
+        jump[plan_idx(p)] = (uint16_t)t;
     }
-    __syncthreads();
+    __syncwarp();
+    // sub-range 31 (or the last one that has positions) is final; stitch the others from the right
+    for (int i = 30; i >= 0; i--) {
+        const uint32_t q0 = (uint32_t)i * kPlanSub + lane * 4;
+        if (q0 < nrel) {
+            uint32_t *w = reinterpret_cast<uint32_t *>(jump + plan_idx(q0));
+            uint32_t v[4] = {w[0] & 0xFFFFu, w[0] >> 16, w[1] & 0xFFFFu, w[1] >> 16};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (q0 + k < nrel && v[k] < nrel) v[k] = jump[plan_idx(v[k])];  // lies in a later, final sub-range
+            w[0] = v[0] | (v[1] << 16);
+            w[1] = v[2] | (v[3] << 16);
+        }
+        __syncwarp();
+    }
+    for (uint32_t it = 0; it < kPB / 128; it++) {
+        const uint32_t q0 = it * 128 + lane * 4;
+        if (q0 >= nrel) break;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(jump + plan_idx(q0));
+        const uint32_t v[4] = {w[0] & 0xFFFFu, w[0] >> 16, w[1] & 0xFFFFu, w[1] >> 16};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = v[k] >= (uint32_t)kPB ? v[k] - kPB : 0u;
+        if (q0 + 4 <= nrel) {
+            *reinterpret_cast<uint2 *>(E0 + start + q0) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+        } else {
+            for (int k = 0; k < 4; k++)
+                if (q0 + k < nrel) E0[start + q0 + k] = (uint16_t)o[k];
+        }
+    }
+}
+__global__ void __launch_bounds__(kPlanWarps * 32) k_parse_exits(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
+                                                                 uint16_t *__restrict__ E0) {
+    __shared__ __align__(16) uint16_t jump[kPlanWarps][kPlanPitch];
+    const size_t block = (size_t)blockIdx.x * kPlanWarps + (threadIdx.x >> 5);
+    if (block * kPB >= n) return;
+    parse_exits_warp(cfg, lo, n, block, E0, jump[threadIdx.x >> 5]);
+}
+
+__device__ __forceinline__ void emit_plan_warp(const ParseCfg &cfg, const uint32_t *__restrict__ lo, size_t n,
+                                               size_t block, const uint64_t *__restrict__ entry0,
+                                               uint16_t *__restrict__ visited, uint64_t *__restrict__ blk_bytes,
+                                               uint16_t *jump) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t start = block * kPB;
+    const uint32_t nrel = (uint32_t)min((size_t)kPB, n - start);
+    plan_load_jumps(cfg, lo, n, start, jump);
+    // ---- speculative orbit of the start of my sub-range
+    const uint32_t sub0 = lane * kPlanSub, sub1 = min(sub0 + kPlanSub, nrel);
+    unsigned long long spec_lo = 0, spec_hi = 0;
+    uint32_t spec_exit = sub0;
     {
-        const uint64_t e = entry0[blockIdx.x];
-        if (threadIdx.x == 0 && e >= start && e - start < nrel) mark[e - start] = 1;
+        uint32_t p = sub0;
+        while (p < sub1) {
+            const uint32_t b = p - sub0;
+            if (b < 64) spec_lo |= 1ull << b;
+            else spec_hi |= 1ull << (b - 64);
+            p += jump[plan_idx(p)];
+        }
+        spec_exit = p;
     }
-    __syncthreads();
-    uint16_t *y = ya, *yn = yb;
-    for (;;) {
-        // scatter: y = jump^(2^r); every marked point marks its 2^r-th successor
-        bool live = false;
-#pragma unroll
-        for (int k = 0; k < kPI; k++) {
-            const uint32_t p = k * kPT + threadIdx.x;
-            const uint32_t v = y[p];
-            if (v < nrel) {
-                if (mark[p]) mark[v] = 1;
-                yn[p] = y[v];
-                live = true;
+    // ---- the true orbit, sub-range by sub-range
+    unsigned long long fin_lo = 0, fin_hi = 0;
+    uint32_t x = nrel;  // where the true orbit stands (relative); nrel: it has left the block
+    {
+        const uint64_t e = entry0[block];
+        if (e >= start && e - start < nrel) x = (uint32_t)(e - start);
+    }
+    for (unsigned j = 0; j < 32 && x < nrel; j++) {
+        if (x / kPlanSub != j) continue;  // the orbit jumps over this sub-range (x is the same in all lanes)
+        uint32_t my_exit = 0;
+        if (lane == j) {
+            unsigned long long path_lo = 0, path_hi = 0;
+            uint32_t p = x;
+            bool merged = false;
+            uint32_t b = 0;
+            while (p < sub1) {
+                b = p - sub0;
+                const bool in_spec = b < 64 ? (spec_lo >> b) & 1ull : (spec_hi >> (b - 64)) & 1ull;
+                if (in_spec) {
+                    merged = true;
+                    break;
+                }
+                if (b < 64) path_lo |= 1ull << b;
+                else path_hi |= 1ull << (b - 64);
+                p += jump[plan_idx(p)];
+            }
+            if (merged) {  // from b on the speculative orbit is the true one
+                const unsigned long long keep_lo = b < 64 ? ~0ull << b : 0ull;
+                const unsigned long long keep_hi = b < 64 ? ~0ull : ~0ull << (b - 64);
+                fin_lo = path_lo | (spec_lo & keep_lo);
+                fin_hi = path_hi | (spec_hi & keep_hi);
+                my_exit = spec_exit;
             } else {
-                yn[p] = (uint16_t)v;
+                fin_lo = path_lo;
+                fin_hi = path_hi;
+                my_exit = p;
             }
         }
-        if (!__syncthreads_or(live)) break;
-        uint16_t *t = y;
-        y = yn;
-        yn = t;
+        x = __shfl_sync(0xffffffffu, my_exit, j);
     }
-    // sizes of the orbit points of my 16 consecutive positions
-    uint32_t bits = 0, bytes = 0;
-    const uint4 mk = *reinterpret_cast<const uint4 *>(mark + p0);
-    const uint32_t mkw[4] = {mk.x, mk.y, mk.z, mk.w};
-#pragma unroll
-    for (int k = 0; k < kPI; k++) {
-        if (p0 + k < nrel && ((mkw[k >> 2] >> ((k & 3) * 8)) & 0xFFu)) {
-            const size_t g = start + p0 + k;
-            bits |= 1u << k;
-            const bool s_ok = cfg.variant == RSN_LZSS_ITER ? sbit(cfg, g) : true;
-            bytes += token_at(cfg, __ldg(lo + g), g, n, s_ok).bytes;
+    // ---- output bytes of my orbit points, visited bits
+    uint32_t bytes = 0;
+    for (int half = 0; half < 2; half++) {
+        unsigned long long m = half ? fin_hi : fin_lo;
+        while (m) {
+            const int k = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const uint32_t p = sub0 + half * 64 + k;
+            const uint32_t jp = jump[plan_idx(p)];
+            if (cfg.variant == RSN_LZSS_ASYNC && jp <= 5) {
+                bytes += jp;  // a literal, or a match too short for any token ("<d,d>" is 5 bytes): its own bytes
+            } else {
+                const size_t g = start + p;
+                const bool s_ok = cfg.variant == RSN_LZSS_ITER ? sbit(cfg, g) : true;
+                bytes += token_at(cfg, __ldg(lo + g), g, n, s_ok).bytes;
+            }
         }
     }
-    visited[(start >> 4) + threadIdx.x] = (uint16_t)bits;
-    uint32_t total;
-    block_exclusive_sum<uint32_t>(bytes, sm, total);
-    if (threadIdx.x == 0) blk_bytes[blockIdx.x] = total;
+    *reinterpret_cast<uint4 *>(visited + (start >> 4) + lane * (kPlanSub / 16)) =
+        make_uint4((uint32_t)fin_lo, (uint32_t)(fin_lo >> 32), (uint32_t)fin_hi, (uint32_t)(fin_hi >> 32));
+#pragma unroll
+    for (int d = 16; d; d >>= 1) bytes += __shfl_down_sync(0xffffffffu, bytes, d);
+    if (lane == 0) blk_bytes[block] = bytes;
 }
-__global__ void __launch_bounds__(kPT) k_emit_plan(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
-                                                   const uint64_t *__restrict__ entry0,
-                                                   uint16_t *__restrict__ visited, uint64_t *__restrict__ blk_bytes) {
-    emit_plan_body(cfg, lo, n, entry0, visited, blk_bytes);
+__global__ void __launch_bounds__(kPlanWarps * 32) k_emit_plan(ParseCfg cfg, const uint32_t *__restrict__ lo, size_t n,
+                                                               const uint64_t *__restrict__ entry0,
+                                                               uint16_t *__restrict__ visited,
+                                                               uint64_t *__restrict__ blk_bytes) {
+    __shared__ __align__(16) uint16_t jump[kPlanWarps][kPlanPitch];
+    const size_t block = (size_t)blockIdx.x * kPlanWarps + (threadIdx.x >> 5);
+    if (block * kPB >= n) return;
+    emit_plan_warp(cfg, lo, n, block, entry0, visited, blk_bytes, jump[threadIdx.x >> 5]);
 }
 
 constexpr int kStage = kPB + 64;  // output bytes of one block never exceed consumed + one token
@@ -593,7 +685,7 @@ static int parse_build_tables(const ParseCfg &cfg, const uint32_t *d_lo, size_t 
         lv.top++;
     }
     RSN_TRY(pp.E0.alloc(pp.blocks * kPB * 2 + 64, s));
-    RSN_LAUNCH(k_parse_exits, (unsigned)pp.blocks, kPT, 0, s, cfg, d_lo, n, pp.E0.as<uint16_t>());
+    RSN_LAUNCH(k_parse_exits, (unsigned)div_up(pp.blocks, kPlanWarps), kPlanWarps * 32, 0, s, cfg, d_lo, n, pp.E0.as<uint16_t>());
     for (int l = 1; l <= lv.top; l++) {
         RSN_TRY(pp.T[l].alloc(lv.regions[l] * (size_t)(J + 1) * 2, s));
         dim3 grid((unsigned)lv.regions[l], (unsigned)div_up((size_t)J + 1, 256));
@@ -620,7 +712,7 @@ static int parse_resolve(const ParseCfg &cfg, const uint32_t *d_lo, size_t n, si
     RSN_TRY(pp.vis.alloc(blocks * (kPB / 16) * 2 + 16, s));
     RSN_TRY(pp.bb.alloc(blocks * 8, s));
     RSN_TRY(pp.bo.alloc((blocks + 1) * 8, s));
-    RSN_LAUNCH(k_emit_plan, (unsigned)blocks, kPT, 0, s, cfg, d_lo, n, pp.entry[0].as<uint64_t>(), pp.vis.as<uint16_t>(),
+    RSN_LAUNCH(k_emit_plan, (unsigned)div_up(blocks, kPlanWarps), kPlanWarps * 32, 0, s, cfg, d_lo, n, pp.entry[0].as<uint64_t>(), pp.vis.as<uint16_t>(),
                pp.bb.as<uint64_t>());
     RSN_TRY(spine_scan_u64(pp.bb.as<uint64_t>(), pp.bo.as<uint64_t>(), pp.bo.as<uint64_t>() + blocks, blocks, s));
     return read_u64(pp.bo.as<uint64_t>() + blocks, total, s);
@@ -817,11 +909,13 @@ __global__ void __launch_bounds__(kTileThreads) kb_escape_apply(LzBatch b) {
     escape_apply_body(f.in, (size_t)f.n, b.tile_off + (size_t)blockIdx.y * b.tc_stride, const_cast<uint8_t *>(f.enc));
 }
 
-__global__ void __launch_bounds__(kPT) kb_parse_exits(LzBatch b) {
+__global__ void __launch_bounds__(kPlanWarps * 32) kb_parse_exits(LzBatch b) {
+    __shared__ __align__(16) uint16_t jump[kPlanWarps][kPlanPitch];
     const LzFile &f = b.files[blockIdx.y];
-    if ((size_t)blockIdx.x * kPB >= f.en) return;
-    parse_exits_body(batch_cfg(f), b.packed + (size_t)blockIdx.y * b.packed_stride, (size_t)f.en,
-                     b.E0 + (size_t)blockIdx.y * b.e0_stride);
+    const size_t block = (size_t)blockIdx.x * kPlanWarps + (threadIdx.x >> 5);
+    if (block * kPB >= f.en) return;
+    parse_exits_warp(batch_cfg(f), b.packed + (size_t)blockIdx.y * b.packed_stride, (size_t)f.en, block,
+                     b.E0 + (size_t)blockIdx.y * b.e0_stride, jump[threadIdx.x >> 5]);
 }
 
 __global__ void kb_parse_up(LzBatch b) {  // grid: (rel chunks, level-1 regions, files)
@@ -852,12 +946,14 @@ __global__ void kb_parse_down(LzBatch b) {  // top == 1: level-1 regions -> bloc
                     b.entry0 + (size_t)blockIdx.y * b.entry0_stride, kBatchFan);
 }
 
-__global__ void __launch_bounds__(kPT) kb_emit_plan(LzBatch b) {
+__global__ void __launch_bounds__(kPlanWarps * 32) kb_emit_plan(LzBatch b) {
+    __shared__ __align__(16) uint16_t jump[kPlanWarps][kPlanPitch];
     const LzFile &f = b.files[blockIdx.y];
-    if ((size_t)blockIdx.x * kPB >= f.en) return;
-    emit_plan_body(batch_cfg(f), b.packed + (size_t)blockIdx.y * b.packed_stride, (size_t)f.en,
+    const size_t block = (size_t)blockIdx.x * kPlanWarps + (threadIdx.x >> 5);
+    if (block * kPB >= f.en) return;
+    emit_plan_warp(batch_cfg(f), b.packed + (size_t)blockIdx.y * b.packed_stride, (size_t)f.en, block,
                    b.entry0 + (size_t)blockIdx.y * b.entry0_stride, b.vis + (size_t)blockIdx.y * b.vis_stride,
-                   b.bb + (size_t)blockIdx.y * b.bb_stride);
+                   b.bb + (size_t)blockIdx.y * b.bb_stride, jump[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(256) kb_emit_finish(LzBatch b) {
@@ -970,12 +1066,12 @@ int lzss_compress_batch(const BatchIO &in, BatchIO &out, int64_t window, cudaStr
             RSN_TRY(lzss_match_tile_batch(b.files, G, ecap, b.window, b.packed, b.packed_stride, s));
         }
     }
-    RSN_LAUNCH(kb_parse_exits, dim3((unsigned)blocks_cap, g), kPT, 0, s, b);
+    RSN_LAUNCH(kb_parse_exits, dim3((unsigned)div_up(blocks_cap, kPlanWarps), g), kPlanWarps * 32, 0, s, b);
     if (b.top)
         RSN_LAUNCH(kb_parse_up, dim3((unsigned)div_up((size_t)window + 1, 256), (unsigned)regions1, g), 256, 0, s, b);
     RSN_LAUNCH(kb_parse_top, (unsigned)div_up(G, 64), 64, 0, s, b, G);
     if (b.top) RSN_LAUNCH(kb_parse_down, dim3((unsigned)div_up(regions1, 128), g), 128, 0, s, b);
-    RSN_LAUNCH(kb_emit_plan, dim3((unsigned)blocks_cap, g), kPT, 0, s, b);
+    RSN_LAUNCH(kb_emit_plan, dim3((unsigned)div_up(blocks_cap, kPlanWarps), g), kPlanWarps * 32, 0, s, b);
     RSN_LAUNCH(kb_emit_finish, g, 256, 0, s, b);
     HostVec<uint64_t> h_outn(G);
     if (!h_outn.data()) return RSN_ERR_NOMEM;
