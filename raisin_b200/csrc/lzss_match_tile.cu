@@ -47,9 +47,39 @@ struct Smem {
     // s[x] == s[x - d] for every staged x in [start, end).  Entries are only ever written after the
     // bytes were compared, the data never changes, so any entry read (even a racing one) is true.
     unsigned long long diag[16 * 8];  // 16 sets (d & 15) x 8 ways
+    unsigned long long mbar;          // mbarrier of the bulk copy that stages the tile
 };
 
 constexpr int kVoteSteps = 8;  // candidates a lane may walk between two votes (3: 5.16 ms, 8: 4.99 ms, 16: 5.29 ms on 64 MiB text)
+
+// The tile's bytes come in with ONE bulk asynchronous copy (cp.async.bulk, the 1-D form of the TMA
+// path): thread 0 arms an mbarrier with the byte count and issues the copy, the copy engine moves
+// global -> shared without passing through registers, and every thread waits on the barrier's phase.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load_tile(void *dst_smem, const void *src_global, uint32_t bytes,
+                                               unsigned long long *mbar) {
+    const uint32_t bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(dst_smem)),
+                     "l"(src_global), "r"(bytes), "r"(bar)
+                     : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+    }
+}
 
 __device__ __forceinline__ uint32_t lds32(const uint8_t *s, uint32_t pos) {
     const uint32_t a = pos & ~3u;
@@ -216,10 +246,8 @@ __device__ __forceinline__ void match_tile_body(const uint8_t *__restrict__ enc,
         const uint32_t nwords = (avail + 3) / 4;
         const uint8_t *g = enc + base;
         if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
-            const uint4 *gv = reinterpret_cast<const uint4 *>(g);
-            uint4 *sv = reinterpret_cast<uint4 *>(sm.s_words);
             const uint32_t fullv = avail / 16;
-            for (uint32_t i = threadIdx.x; i < fullv; i += THREADS) sv[i] = __ldg(gv + i);
+            if (fullv) bulk_load_tile(sm.s_words, g, fullv * 16, &sm.mbar);
             for (uint32_t i = fullv * 4 + threadIdx.x; i < nwords; i += THREADS) {
                 uint32_t v = 0;
                 for (uint32_t b = 0; b < 4; b++)

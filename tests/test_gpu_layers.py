@@ -180,6 +180,55 @@ def test_batch_device_buffers(rsn, oracle):
         lib.rsn_dev_free(outs[i], None)
 
 
+def test_batch_device_buffers_decompress_stages_header_prefixes(rsn, oracle):
+    """Device-resident Huffman decode batches fetch growing prefixes of the streams for the header
+    parser (4 KiB, 64 KiB, the rest): headers that end inside each round, a separator that straddles a
+    round boundary, alphabets beyond the device tree builder, streams without a separator."""
+    import ctypes as C
+
+    import torch
+
+    lib = rsn._lib.lib()
+    plain = [synth.batch_file(0, 50000),                      # text: header of a few hundred bytes
+             synth.batch_file(2, 200000),                     # random bytes: ~2 800 records, second round
+             "".join(chr(0x800 + (i * 104729) % 40000) for i in range(30000)).encode(),  # > 64 KiB of header
+             "".join(chr(0x100 + (i * 7919) % 5000) for i in range(6000)).encode(),
+             b"abc" * 3000]
+    streams = [oracle.huff_compress(f) for f in plain]
+    # a header whose 5C 0A sits on the 4096-byte boundary of the first round: pad the alphabet until it does
+    for extra in range(200, 1400):
+        f = "".join(chr(0x100 + i) for i in range(extra)).encode() + b"x" * 50
+        st = oracle.huff_compress(f)
+        if st.find(b"\\\n") in (4094, 4095, 4096):
+            plain.append(f)
+            streams.append(st)
+    assert len(streams) > 5
+    streams += [b"no separator in here at all" * 400, b"12|a3|b\\\n", b""]  # bad streams fail alone
+    want = rsn.engine.batch(streams, ["huffman"], False, workers=2)  # host-buffer path
+    for f, w in zip(plain, want):
+        try:
+            ref = oracle.huff_decompress(oracle.huff_compress(f), strict=False)
+        except Exception:
+            ref = None
+        assert w == ref
+    tens = [torch.frombuffer(bytearray(st if st else b"\0"), dtype=torch.uint8).cuda() for st in streams]
+    torch.cuda.synchronize()
+    n = len(streams)
+    ins = (C.c_void_p * n)(*[t.data_ptr() for t in tens])
+    ns = (C.c_size_t * n)(*[len(st) for st in streams])
+    outs, out_ns, rcs = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+    lib.rsn_batch_layers(b"huffman", 0, n, ins, ns, outs, out_ns, rcs, 3, 1)
+    for i in range(n):
+        if want[i] is None:
+            assert rcs[i] != 0, i
+            continue
+        assert rcs[i] == 0, (i, rcs[i])
+        h = (C.c_uint8 * max(1, out_ns[i]))()
+        rsn._lib.check(lib.rsn_dev_download(outs[i], out_ns[i], h, None))
+        assert bytes(h)[:out_ns[i]] == want[i], i
+        lib.rsn_dev_free(outs[i], None)
+
+
 def test_concurrent_callers(rsn, oracle):
     """engine.BenchmarkSuite calls the codecs from several goroutines at once (engine.go:235-244):
     the C ABI must be re-entrant from multiple OS threads (ctypes releases the GIL during calls)."""

@@ -34,11 +34,14 @@ def mnem(ins):
 
 
 print("# r2: SASS of the library's kernels (`cuobjdump -sass raisin_b200/libraisin_b200.so`, sm_100a)\n")
-print("Every kernel is integer / byte work: no HMMA / UTCMMA (tensor), no UBLKCP / UTMALDG (bulk async / TMA) anywhere — "
-      "tiles are staged with 16-byte `LDG.E.128` + `STS.128`.  The kernels are bound by shared-memory round trips and "
-      "integer issue (see the ncu summaries), not by how bytes reach shared memory.\n")
-print("| kernel | SASS instr. | LDG | STG | LDS | STS | ATOMS/ATOMG/RED | SHFL/VOTE/MATCH | BAR | top mnemonics |")
-print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---|")
+print("Every kernel is integer / byte work: no HMMA / UTCMMA (tensor) anywhere.  The match search stages its 16 KB tile "
+      "with one bulk asynchronous copy (`UBLKCP.S.G` = `cp.async.bulk.shared::cluster.global`, completion on an mbarrier: "
+      "`SYNCS.ARRIVE.TRANS64` / `SYNCS.PHASECHK.TRANS64.TRYWAIT`); it measures the same as the `LDG.E.128` + `STS.128` "
+      "loop it replaced (64 MiB text: 4.864 ms against 4.871), because the kernels are bound by shared-memory round trips "
+      "and integer issue (see the ncu summaries), not by how bytes reach shared memory.  The other kernels stream their "
+      "tiles through registers with 16-byte loads.\n")
+print("| kernel | SASS instr. | LDG | STG | LDS | STS | ATOMS/ATOMG/RED | SHFL/VOTE/MATCH | BAR | UBLKCP/SYNCS | top mnemonics |")
+print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|")
 want = ["k_match_tile", "kb_match_tile", "k_parse_exits", "k_emit_plan", "k_emit_write", "k_escape_apply", "k_tok_tile", "k_resolve4",
         "k_rune_hist", "k_enc_count", "k_enc_write", "k_hdec_init", "k_hdec_sync", "k_hdec_write", "kb_huff_tree", "kb_big_gather",
         "k_byte_hist"]
@@ -56,8 +59,8 @@ for f, ins in funcs.items():
 
     top = ", ".join(f"{k} {v}" for k, v in c.most_common(6))
     rows.append((want.index(base), f"| `{short}` | {len(ins)} | {tot('LDG')} | {tot('STG')} | {tot('LDS')} | {tot('STS')} | "
-                 f"{tot('ATOMS', 'ATOMG', 'RED')} | {tot('SHFL', 'VOTE', 'MATCH')} | {tot('BAR')} | {top} |"))
-    bad = [k for k in c if k.startswith(("HMMA", "UTCMMA", "UBLKCP", "UTMA", "LDGSTS"))]
+                 f"{tot('ATOMS', 'ATOMG', 'RED')} | {tot('SHFL', 'VOTE', 'MATCH')} | {tot('BAR')} | {tot('UBLKCP', 'SYNCS')} | {top} |"))
+    bad = [k for k in c if k.startswith(("HMMA", "UTCMMA"))]
     assert not bad, bad
 for _, r in sorted(rows):
     print(r)
