@@ -573,22 +573,33 @@ __device__ __forceinline__ void emit_write_body(const ParseCfg &cfg, const uint8
                                                 const uint16_t *__restrict__ visited,
                                                 const uint64_t *__restrict__ blk_off, uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint8_t stage[kStage];
+    __shared__ uint16_t tokpos[kPB];  // the block's orbit points, in order
     __shared__ uint32_t sm[33];
     const size_t start = (size_t)blockIdx.x * kPB;
     const uint32_t p0 = threadIdx.x * kPI;
     const uint32_t bits = visited[(start >> 4) + threadIdx.x];
+    // Orbit points are spread unevenly over the positions (16 in a run of literals, one or two
+    // inside matches): with a thread formatting the points of ITS 16 positions a warp waited for its
+    // busiest lane (11 of 32 lanes active, 6 warp instructions per position).  The points are
+    // compacted first, and every thread takes an equal, contiguous share of them.
+    uint32_t ntok;
+    {
+        uint32_t at = block_exclusive_sum<uint32_t>((uint32_t)__popc(bits), sm, ntok);
+        for (uint32_t b = bits; b; b &= b - 1) tokpos[at++] = (uint16_t)(p0 + __ffs(b) - 1);
+    }
+    __syncthreads();
+    const uint32_t per = (ntok + kPT - 1) / kPT;
+    const uint32_t k_lo = min(ntok, threadIdx.x * per), k_hi = min(ntok, k_lo + per);
     uint32_t bytes = 0;
-    for (uint32_t b = bits; b; b &= b - 1) {
-        const int k = __ffs(b) - 1;
-        const size_t g = start + p0 + k;
+    for (uint32_t k = k_lo; k < k_hi; k++) {
+        const size_t g = start + tokpos[k];
         const bool s_ok = cfg.variant == RSN_LZSS_ITER ? sbit(cfg, g) : true;
         bytes += token_at(cfg, __ldg(lo + g), g, n, s_ok).bytes;
     }
     uint32_t total;
     uint32_t pos = block_exclusive_sum<uint32_t>(bytes, sm, total);
-    for (uint32_t b = bits; b; b &= b - 1) {
-        const int k = __ffs(b) - 1;
-        const size_t g = start + p0 + k;
+    for (uint32_t k = k_lo; k < k_hi; k++) {
+        const size_t g = start + tokpos[k];
         const bool s_ok = cfg.variant == RSN_LZSS_ITER ? sbit(cfg, g) : true;
         const Tok t = token_at(cfg, __ldg(lo + g), g, n, s_ok);
         uint8_t *o = stage + pos;
