@@ -741,8 +741,10 @@ cudaError_t copy_many(void *const *dsts, const void *const *srcs, const size_t *
         const cudaError_t e = cudaMemcpyBatchAsync(d.data(), sr.data(), sz.data(), d.size(), &at, &first, 1, &fail, s);
         if (e == cudaSuccess) return e;
         cudaGetLastError();
-        if (e == cudaErrorNotSupported) batch_ok.store(false);  // older driver: one by one from now on
-        else if (e != cudaErrorInvalidValue) return e;           // (a kind of memory the batch call refuses: this batch one by one)
+        // an older driver: one by one from now on; anything else the batch call refuses (a kind of
+        // memory, an attribute): this batch one by one, and the plain copies report what is wrong
+        if (e == cudaErrorNotSupported || e == cudaErrorCallRequiresNewerDriver || e == cudaErrorInsufficientDriver)
+            batch_ok.store(false);
     }
     for (size_t i = 0; i < d.size(); i++) {
         const cudaError_t e = cudaMemcpyAsync(d[i], sr[i], sz[i], cudaMemcpyDefault, s);
