@@ -133,14 +133,16 @@ int rsn_benchmark_file(const char *algorithms, const uint8_t *in, size_t n, rsn_
  * dimension), so a small file costs no kernel launches or synchronisations of its own; groups, and
  * the files that go one by one (empty, larger than 4 MiB), are spread over `workers` host threads
  * (0 = default), each with its own CUDA stream.  out[i]/out_n[i] receive library-owned buffers
- * (rsn_free each); rcs[i] (optional) the per-file code: a file the reference would panic on fails
- * alone.  The per-file host work of a group (leaf order, header bytes) uses cores / workers helper
+ * (rsn_free each, in any order: the results of a group share one pinned block that goes back to the
+ * pool with its last part); rcs[i] (optional) the per-file code: a file the reference would panic on
+ * fails alone.  The per-file host work of a group (leaf order, header bytes) uses cores / workers helper
  * threads; RSN_HOST_CORES in the environment overrides the core count (set it to cores / ranks when
  * several ranks share a box).  Returns RSN_OK or the first failing file's code.  With device != 0 the in/out pointers
  * are device pointers on the calling thread's device: inputs are used in place (grouped like host
  * files when 16-byte aligned, otherwise one by one), every result is its own device buffer
  * (release with rsn_dev_free(p, NULL)); nothing crosses PCIe except sizes — and, when the first
- * layer to undo is "huffman", a host copy of the streams for the header parser.
+ * layer to undo is "huffman", the header of every stream (up to the byte after its first 5C 0A) for
+ * the header parser.
  */
 int rsn_batch_layers(const char *algorithms, int compress, size_t count, const uint8_t *const *in, const size_t *in_n,
                      uint8_t **out, size_t *out_n, int *rcs, int workers, int device);
