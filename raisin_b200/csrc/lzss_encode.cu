@@ -151,42 +151,6 @@ __device__ __forceinline__ bool sbit(const ParseCfg &cfg, size_t g) {
     return (__ldg(cfg.sbits + (g >> 5)) >> (g & 31)) & 1u;
 }
 
-// jump[p] for the block's positions; positions >= n get 1.
-__device__ __forceinline__ void load_jumps(const ParseCfg &cfg, const uint32_t *__restrict__ lo, size_t start,
-                                           size_t n, uint16_t *jump) {
-    const uint32_t p0 = threadIdx.x * kPI;
-    uint32_t L[kPI];
-    if (start + p0 + kPI <= n) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(lo + start + p0);
-#pragma unroll
-        for (int q = 0; q < kPI / 4; q++) {
-            const uint4 v = __ldg(src + q);
-            L[4 * q] = v.x >> 16;
-            L[4 * q + 1] = v.y >> 16;
-            L[4 * q + 2] = v.z >> 16;
-            L[4 * q + 3] = v.w >> 16;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < kPI; k++) L[k] = start + p0 + k < n ? (__ldg(lo + start + p0 + k) >> 16) : 0u;
-    }
-    uint32_t sb = 0;
-    if (cfg.variant == RSN_LZSS_ITER) {  // 16 consecutive S bits (start + p0 is a multiple of 16)
-        sb = (__ldg(cfg.sbits + ((start + p0) >> 5)) >> ((start + p0) & 31)) & 0xFFFFu;
-    }
-    uint32_t w[kPI / 2];
-#pragma unroll
-    for (int k = 0; k < kPI; k++) {
-        uint32_t j = L[k] ? L[k] : 1u;
-        if (cfg.variant == RSN_LZSS_ITER) j = ((sb >> k) & 1u) ? j + 1 : 1u;
-        if (k & 1) w[k >> 1] |= j << 16;
-        else w[k >> 1] = j;
-    }
-    uint4 *dst = reinterpret_cast<uint4 *>(jump + p0);  // jump[] is 16-byte aligned, p0 a multiple of 16
-    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
-
 struct ParseLevels {
     int top;                 // highest level; level l regions have size kPB * kFan^l
     size_t regions[8];       // region count per level
