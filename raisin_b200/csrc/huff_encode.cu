@@ -560,14 +560,20 @@ void henc_host_plan(const uint32_t *hist, uint32_t *big, size_t big_n, HencHost 
         if (hist[r]) leaves.push_back(HuffLeaf{(int64_t)hist[r], r});
     sort_runes(big, big_n);
     size_t nbig = 0;
+    bool fffd_pending = hist[256] != 0;  // U+FFFD is counted apart; it goes in at its place in rune order
     for (size_t i = 0; i < big_n;) {
         size_t j = i;
         while (j < big_n && big[j] == big[i]) j++;
+        if (fffd_pending && big[i] > 0xFFFDu) {
+            leaves.push_back(HuffLeaf{(int64_t)hist[256], 0xFFFD});
+            nbig++;
+            fffd_pending = false;
+        }
         leaves.push_back(HuffLeaf{(int64_t)(j - i), (int32_t)big[i]});
         nbig++;
         i = j;
     }
-    if (hist[256]) {
+    if (fffd_pending) {
         leaves.push_back(HuffLeaf{(int64_t)hist[256], 0xFFFD});
         nbig++;
     }

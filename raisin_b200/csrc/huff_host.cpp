@@ -191,19 +191,12 @@ bool huff_codes(const HuffTree &t, std::vector<HuffCode> &codes) {
     return ok;
 }
 
-static void put_dec(std::vector<uint8_t> &o, uint64_t v) {
-    char tmp[24];
-    int k = 0;
-    do {
-        tmp[k++] = (char)('0' + v % 10);
-        v /= 10;
-    } while (v);
-    while (k--) o.push_back((uint8_t)tmp[k]);
-}
-
 void huff_header(const std::vector<HuffLeaf> &leaves_in, std::vector<uint8_t> &hdr) {
     std::vector<HuffLeaf> lv(leaves_in);
-    {
+    // the batch path hands the leaves over in ascending rune order already: nothing to sort then
+    bool ascending = true;
+    for (size_t i = 1; i < lv.size() && ascending; i++) ascending = lv[i - 1].rune < lv[i].rune;
+    if (!ascending) {
         bool packable = true;
         for (const HuffLeaf &l : lv)
             if (l.freq < 0 || l.freq >= ((int64_t)1 << 42)) packable = false;
@@ -218,19 +211,29 @@ void huff_header(const std::vector<HuffLeaf> &leaves_in, std::vector<uint8_t> &h
         }
     }
     if (lv.size() >= 2 && lv.back().rune == 0x5C) std::swap(lv[lv.size() - 1], lv[lv.size() - 2]);
-    hdr.clear();
+    // a record is at most 20 digits + '|' + 4 bytes: format into a buffer of that size and trim
+    hdr.resize(lv.size() * 25);
+    uint8_t *o = hdr.data();
     for (const HuffLeaf &l : lv) {
-        put_dec(hdr, (uint64_t)l.freq);
-        hdr.push_back('|');
+        uint64_t v = (uint64_t)l.freq;
+        char tmp[24];
+        int k = 0;
+        do {
+            tmp[k++] = (char)('0' + v % 10);
+            v /= 10;
+        } while (v);
+        while (k--) *o++ = (uint8_t)tmp[k];
+        *o++ = '|';
         if (l.rune == 10) {  // huffman.go:315-317
-            hdr.push_back('\\');
-            hdr.push_back('n');
+            *o++ = '\\';
+            *o++ = 'n';
+        } else if (l.rune >= 0 && l.rune < 0x80) {
+            *o++ = (uint8_t)l.rune;
         } else {
-            uint8_t u[4];
-            int w = utf8_encode(l.rune, u);
-            hdr.insert(hdr.end(), u, u + w);
+            o += utf8_encode(l.rune, o);
         }
     }
+    hdr.resize((size_t)(o - hdr.data()));
 }
 
 // strconv.Atoi over a digit-only string, error dropped: empty => 0, overflow => MaxInt64.
@@ -262,6 +265,7 @@ bool huff_parse_header(const uint8_t *h, size_t hn, std::vector<HuffLeaf> &leave
     // 10 MB of table per call would dominate small files.
     std::vector<HuffLeaf> rec;
     std::vector<uint8_t> temp;
+    rec.reserve(hn / 4 + 1);
     for (size_t i = 0; i < hn; i++) {
         if (h[i] != '|') {
             if (h[i] >= '0' && h[i] <= '9') temp.push_back(h[i]);
@@ -289,6 +293,16 @@ bool huff_parse_header(const uint8_t *h, size_t hn, std::vector<HuffLeaf> &leave
     }
     leaves.clear();
     const size_t k = rec.size();
+    {
+        // records in strictly ascending rune order (every header this library writes, bar the swap
+        // that keeps a backslash off the end): no duplicates, and the order asked for
+        bool ascending = true;
+        for (size_t i = 1; i < k && ascending; i++) ascending = rec[i - 1].rune < rec[i].rune;
+        if (ascending) {
+            leaves.swap(rec);
+            return true;
+        }
+    }
     if (k > ((size_t)1 << 16)) {
         std::vector<uint32_t> last(0x110000, 0);  // 1 + index of the last record of the rune
         for (size_t i = 0; i < k; i++) last[rec[i].rune] = (uint32_t)i + 1;

@@ -77,6 +77,11 @@ def test_header_matches_oracle(harness):
         text = f"{len(runes)}\n" + "".join(f"{r} {f}\n" for r, f in zip(runes, freqs))
         got_hdr = bytes.fromhex(run(harness, "codes", text).splitlines()[-1].split()[1])
         assert got_hdr == want_hdr, k
+        # the same leaves handed over in ascending rune order (what the batch path does: no sort inside)
+        pairs = sorted(zip(runes, freqs))
+        text = f"{len(pairs)}\n" + "".join(f"{r} {f}\n" for r, f in pairs)
+        got_hdr = bytes.fromhex(run(harness, "codes", text).splitlines()[-1].split()[1])
+        assert got_hdr == want_hdr, k
 
 
 def test_header_parse_matches_decode_tree(harness):
